@@ -1,0 +1,192 @@
+"""ctypes front-ends for the CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+* `Oracle`    -> oracle/liboracle.so   (plain-C fp64 restatement, svn_oracle.c)
+* `Reference` -> oracle/_ref/libsvnicp_ref.so (the reference's own sources, CPU device swap)
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+
+
+class Params(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("lr", C.c_double), ("max_dist", C.c_double),
+                ("check_early_stop", C.c_int), ("convergence_threshold", C.c_double),
+                ("knn_count", C.c_int), ("svn_full_grad", C.c_int)]
+
+
+def make_params(iterations=30, lr=1.0, max_dist=3.0, check_early_stop=False, convergence_threshold=5e-4,
+                knn_count=100, svn_full_grad=True) -> Params:
+    return Params(int(iterations), float(lr), float(max_dist), int(bool(check_early_stop)),
+                  float(convergence_threshold), int(knn_count), int(bool(svn_full_grad)))
+
+
+class Dumps(C.Structure):
+    _fields_ = [("corr_idx", C.c_void_p), ("corr_mask", C.c_void_p), ("H", C.c_void_p), ("b", C.c_void_p),
+                ("delta", C.c_void_p), ("x_before", C.c_void_p), ("x_after", C.c_void_p), ("bandwidth", C.c_void_p)]
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(HERE, "liboracle.so")
+    src = os.path.join(HERE, "svn_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(build())
+        self.lib.oracle_rbf_kernel.restype = C.c_double
+        self.lib.oracle_num_threads.restype = C.c_int
+
+    def num_threads(self):
+        return self.lib.oracle_num_threads()
+
+    def set_num_threads(self, n):
+        self.lib.oracle_set_num_threads(int(n))
+
+    def so3_exp(self, r):
+        R = np.zeros(9)
+        Jl = np.zeros(9)
+        with np.errstate(all="ignore"):
+            self.lib.oracle_so3_exp(_ptr(_f64(r)), _ptr(R), _ptr(Jl))
+        return R.reshape(3, 3), Jl.reshape(3, 3)
+
+    def so3_log(self, R):
+        w = np.zeros(3)
+        self.lib.oracle_so3_log(_ptr(_f64(R).reshape(-1)), _ptr(w))
+        return w
+
+    def transform_q0(self, src, R0, t0):
+        src = _f64(src)
+        q0 = np.empty_like(src)
+        self.lib.oracle_transform_q0(_ptr(src), C.c_int64(len(src)), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(q0))
+        return q0
+
+    def knn_mink(self, q, tgt, K):
+        q, tgt = _f64(q), _f64(tgt)
+        idx = np.zeros((len(q), K), dtype=np.int64)
+        dist = np.zeros((len(q), K), dtype=np.float64)
+        self.lib.oracle_knn_mink(_ptr(q), C.c_int64(len(q)), _ptr(tgt), C.c_int64(len(tgt)), C.c_int(K), _ptr(idx), _ptr(dist))
+        return idx, dist
+
+    def gn(self, R, t, R0, t0, src, tgt, cand_idx, max_dist, want_corr=False):
+        R, t, src, tgt = _f64(R), _f64(t), _f64(src), _f64(tgt)
+        P = len(R)
+        cand_idx = np.ascontiguousarray(cand_idx, dtype=np.int64)
+        K = cand_idx.shape[1]
+        H = np.zeros((P, 6, 6))
+        b = np.zeros((P, 6))
+        ci = np.zeros((P, len(src)), dtype=np.int32) if want_corr else None
+        cm = np.zeros((P, len(src)), dtype=np.uint8) if want_corr else None
+        self.lib.oracle_gn(_ptr(R), _ptr(t), C.c_int(P), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(src), C.c_int64(len(src)),
+                           _ptr(tgt), _ptr(cand_idx), C.c_int(K), C.c_double(max_dist), _ptr(H), _ptr(b), _ptr(ci), _ptr(cm))
+        return (H, b, ci, cm) if want_corr else (H, b)
+
+    def stein_step(self, x, H, b, full=True, lr=1.0):
+        x, H, b = _f64(x), _f64(H), _f64(b)
+        P = len(x)
+        d = np.zeros((P, 6))
+        h = C.c_double(0)
+        self.lib.oracle_stein_step(_ptr(x), _ptr(H), _ptr(b), C.c_int(P), C.c_int(int(full)), C.c_double(lr), _ptr(d), C.byref(h))
+        return d, h.value
+
+    def pose_update(self, R, t, delta):
+        R, t, delta = _f64(R).copy(), _f64(t).copy(), _f64(delta)
+        with np.errstate(all="ignore"):
+            self.lib.oracle_pose_update(_ptr(R), _ptr(t), _ptr(delta), C.c_int(len(R)))
+        return R, t
+
+    def rbf_kernel(self, x):
+        x = _f64(x)
+        P = len(x)
+        K = np.zeros((P, P))
+        h = self.lib.oracle_rbf_kernel(_ptr(x), C.c_int(P), _ptr(K))
+        return K, h
+
+    def align(self, prm: Params, src, tgt, init_pose, R0, t0, dumps=()):
+        """Whole scan.  dumps: subset of Dumps field names to record."""
+        src, tgt, init_pose = _f64(src), _f64(tgt), _f64(init_pose)
+        P, I, ns = init_pose.shape[1], prm.iterations, len(src)
+        out = dict(particles=np.zeros((6, P)), mean=np.zeros(6), var=np.zeros(6), cov=np.zeros((6, 6)),
+                   weights=np.zeros(P), history=np.zeros((I, 6, P), dtype=np.float32),
+                   cand_idx=np.zeros((ns, prm.knn_count), dtype=np.int64))
+        shapes = dict(corr_idx=((I, P, ns), np.int32), corr_mask=((I, P, ns), np.uint8), H=((I, P, 6, 6), np.float64),
+                      b=((I, P, 6), np.float64), delta=((I, P, 6), np.float64), x_before=((I, P, 6), np.float64),
+                      x_after=((I, P, 6), np.float64), bandwidth=((I,), np.float64))
+        d = Dumps()
+        for name in dumps:
+            shp, dt = shapes[name]
+            out[name] = np.zeros(shp, dtype=dt)
+            setattr(d, name, out[name].ctypes.data)
+        it = C.c_int(0)
+        state = self.lib.oracle_align(C.byref(prm), _ptr(src), C.c_int64(ns), _ptr(tgt), C.c_int64(len(tgt)), _ptr(init_pose),
+                                      C.c_int(P), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(out["particles"]), _ptr(out["mean"]),
+                                      _ptr(out["var"]), _ptr(out["cov"]), _ptr(out["weights"]), _ptr(out["history"]),
+                                      C.byref(it), _ptr(out["cand_idx"]), C.byref(d))
+        out["state"] = state
+        out["iters_done"] = it.value
+        return out
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libsvnicp_ref.so"))
+
+
+class Reference:
+    """The reference's own registration classes (CPU device swap).  One (P, threshold) per PROCESS
+    (function-static tensors, SVNICP.cpp:42,167) -- run each configuration in a fresh subprocess."""
+
+    def __init__(self):
+        import torch  # noqa: F401  (libtorch must be loaded first)
+        self.lib = C.CDLL(os.path.join(HERE, "_ref", "libsvnicp_ref.so"))
+        self.lib.ref_num_threads.restype = C.c_int
+
+    def num_threads(self):
+        return self.lib.ref_num_threads()
+
+    def set_num_threads(self, n):
+        self.lib.ref_set_num_threads(int(n))
+
+    def scan(self, prm: Params, src, tgt, init_pose, R0, t0):
+        src, tgt, init_pose = _f64(src), _f64(tgt), _f64(init_pose)
+        P, I = init_pose.shape[1], prm.iterations
+        out = dict(particles=np.zeros((6, P)), mean=np.zeros(6), var=np.zeros(6), cov=np.zeros((6, 6)),
+                   weights=np.zeros(P), history=np.zeros((I, 6, P), dtype=np.float32), seconds=np.zeros(3))
+        out["state"] = self.lib.ref_scan(C.byref(prm), _ptr(src), C.c_int64(len(src)), _ptr(tgt), C.c_int64(len(tgt)),
+                                         _ptr(init_pose), C.c_int(P), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(out["particles"]),
+                                         _ptr(out["mean"]), _ptr(out["var"]), _ptr(out["cov"]), _ptr(out["weights"]),
+                                         _ptr(out["history"]), _ptr(out["seconds"]))
+        return out
+
+    def scan_steps(self, prm: Params, src, tgt, init_pose, R0, t0, steps, want=("x_after", "H", "b", "tgt_paired", "cand_idx")):
+        src, tgt, init_pose = _f64(src), _f64(tgt), _f64(init_pose)
+        P, ns = init_pose.shape[1], len(src)
+        shapes = dict(x_after=((steps, 6, P), np.float64), H=((steps, P, 6, 6), np.float64), b=((steps, P, 6), np.float64),
+                      tgt_paired=((steps, P, ns, 3), np.float64), src_tr=((steps, P, ns, 3), np.float64),
+                      cand_idx=((ns, prm.knn_count), np.int64))
+        out = {k: np.zeros(*shapes[k]) for k in want}
+        out.update(particles=np.zeros((6, P)), mean=np.zeros(6), var=np.zeros(6), cov=np.zeros((6, 6)))
+        g = lambda k: _ptr(out.get(k))
+        out["state"] = self.lib.ref_scan_steps(C.byref(prm), _ptr(src), C.c_int64(ns), _ptr(tgt), C.c_int64(len(tgt)),
+                                               _ptr(init_pose), C.c_int(P), _ptr(_f64(R0)), _ptr(_f64(t0)), C.c_int(steps),
+                                               g("x_after"), g("H"), g("b"), g("tgt_paired"), g("src_tr"), g("cand_idx"),
+                                               _ptr(out["particles"]), _ptr(out["mean"]), _ptr(out["var"]), _ptr(out["cov"]))
+        return out
