@@ -1,0 +1,158 @@
+/*
+ * svnicp_b200.h -- C ABI of the B200-native SVN-ICP registration inner loop.
+ *
+ * This is the drop-in boundary for the reference's registration-class interface
+ * (svnicp::SVGDICP / svnicp::SVNICP, reference svn-icp/include/core/SVGDICP.h:64-211 and
+ * SVNICP.h:29-80).  Each entry point names the reference member it replaces.  Plain pointers
+ * and sizes only: no torch, no C++ types, no exceptions cross this boundary.  A header-only C++
+ * mirror of the reference classes on top of this ABI is in
+ * svn_icp_b200/include/svnicp/SVNICP.hpp; INTEGRATION.md shows the binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - one handle per caller thread (the reference class is not thread safe either,
+ *     OdometryPipeline.cpp:106-110); calls on a handle are blocking unless stated.
+ *   - every function returns SVNICP_OK (0) or a negative svnicp_status; svnicp_align returns the
+ *     reference's SteinICPState (1 = ALIGN_SUCCESS, 2 = NO_OPTIMIZER) or a negative status.
+ *     svnicp_last_error() gives the message (CUDA / NCCL error text included).
+ *   - there is NO CPU fallback: without a CUDA device svnicp_create fails with
+ *     SVNICP_ERR_NO_DEVICE.
+ *   - clouds are float64 [N][3] row-major exactly like the reference's tensors
+ *     (SVGDICP.h:207 data_type = kFloat64); particles are [6][P] component-major
+ *     (x,y,z,rx,ry,rz rows), the layout of init_pose [6,P,1] and of get_particles()
+ *     (SVGDICP.cpp:515-520).
+ */
+#ifndef SVNICP_B200_H
+#define SVNICP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVNICP_B200_ABI_VERSION 1
+
+typedef struct svnicp_handle_t *svnicp_handle;
+
+typedef enum {
+  SVNICP_OK = 0,
+  SVNICP_ERR_INVALID = -1,    /* bad argument / call order                       */
+  SVNICP_ERR_NO_DEVICE = -2,  /* no CUDA device or wrong architecture (need sm_100) */
+  SVNICP_ERR_CUDA = -3,       /* CUDA runtime error, see svnicp_last_error       */
+  SVNICP_ERR_NCCL = -4,       /* NCCL error / libnccl not loadable               */
+  SVNICP_ERR_OOM = -5
+} svnicp_status;
+
+/* SteinICPState, SVGDICP.h:59-62 */
+#define SVNICP_ALIGN_SUCCESS 1
+#define SVNICP_NO_OPTIMIZER 2
+
+/* class_type switch of OdometryPipeline.cpp:282-288 */
+#define SVNICP_CLASS_SVNICP 0
+#define SVNICP_CLASS_SVGDICP 1
+
+/* SteinICPParam (SVGDICP.h:41-57) + ParticleWeightOpt (SVNICP.h:25-27); same defaults. */
+typedef struct {
+  int32_t iterations;            /* 50   */
+  int32_t use_minibatch;         /* 0    (never enabled by the reference, SVGDICP.cpp:178-185) */
+  int32_t batch_size;            /* 50   (overwritten with N_s, SVGDICP.cpp:181)               */
+  double lr;                     /* 0.02 */
+  double max_dist;               /* 1.0  */
+  int32_t normalize_cloud;       /* 1    (unused by the hot path)                              */
+  char optimizer[16];            /* "Adam" | "RMSprop" | "SGD" | "Adagrad" (SVGDICP only)     */
+  int32_t check_early_stop;      /* 0    */
+  int32_t convergence_steps;     /* 5    (unused by the hot path)                              */
+  double convergence_threshold;  /* 1e-5 */
+  int32_t KNN_count;             /* 100  */
+  int32_t SVN_full_grad;         /* 1    */
+  int32_t use_weight_mean;       /* 0    ParticleWeightOpt                                     */
+  /* ---- extensions (0 = default); not in the reference ---- */
+  double grid_cell;              /* candidate-builder voxel-hash cell edge in metres (0 -> 1.5) */
+  int32_t debug_corr;            /* 1 -> keep per-(particle,point) correspondences of the LAST executed
+                                    iteration for svnicp_get_correspondences (parity tests)    */
+} svnicp_params;
+
+/* Fill with the defaults of SteinICPParam (SVGDICP.h:41-57). */
+void svnicp_default_params(svnicp_params *p);
+
+int svnicp_abi_version(void);
+
+/* SVNICP::SVNICP / SVGDICP::SVGDICP (SVNICP.cpp:20-38, SVGDICP.cpp:22-44).
+ * init_pose: [6][P] host doubles, may be NULL (zeros).  device: CUDA ordinal (-1 = current). */
+int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_count, const double *init_pose,
+                  int class_type, int device);
+void svnicp_destroy(svnicp_handle h);
+const char *svnicp_last_error(svnicp_handle h); /* h may be NULL: last creation error */
+
+/* Launch everything on this CUDA stream (cudaStream_t as void*; NULL = the handle's own stream).
+ * The reference uses the current CUDA stream (knn.cu:331). */
+int svnicp_set_stream(svnicp_handle h, void *cuda_stream);
+
+/* Particle sharding across the GPUs of one box (no reference counterpart):
+ * every rank owns particles [rank*P/n, (rank+1)*P/n) and one ncclAllGather per iteration carries
+ * the packed per-particle record.  unique_id: 128 bytes from svnicp_nccl_unique_id on rank 0,
+ * distributed by the caller (MPI / torch.distributed / files).  libnccl.so.2 is dlopen'ed. */
+int svnicp_nccl_unique_id(void *id128);
+int svnicp_init_sharding(svnicp_handle h, const void *unique_id128, int rank, int n_ranks);
+
+/* SVGDICP::add_cloud (SVGDICP.cpp:46-62).  source [n_s][3], target [n_t][3], init_pose [6][P]
+ * (host).  Clouds are copied (the reference clones, :55-56).  *_device: 1 if the cloud pointer is
+ * device memory on the handle's GPU. */
+int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int source_on_device, const double *target,
+                     int64_t n_t, int target_on_device, const double *init_pose);
+
+/* SVGDICP::set_initial_mean (SVGDICP.h:102-110).  R0 row-major 3x3 (= gtsam Rot3::matrix()), t0[3]. */
+int svnicp_set_initial_mean(svnicp_handle h, const double R0[9], const double t0[3]);
+
+/* SVNICP::stein_align / SVGDICP::stein_align (SVNICP.cpp:41-114, SVGDICP.cpp:66-140).  Blocking. */
+int svnicp_align(svnicp_handle h);
+
+/* getters: SVNICP.cpp:281-308, SVGDICP.cpp:497-534, SVGDICP.h:94-100 */
+int svnicp_get_transformation(svnicp_handle h, double out6[6]);
+int svnicp_get_distribution(svnicp_handle h, double out6[6]);
+int svnicp_get_cov_matrix(svnicp_handle h, double out36[36]);
+int svnicp_get_particles(svnicp_handle h, double *out_6xP);
+int svnicp_get_particle_weight(svnicp_handle h, double *out_P);
+int svnicp_get_particle_history(svnicp_handle h, float *out_Ix6xP, int32_t *rows /* = iterations */);
+int svnicp_get_runtime(svnicp_handle h, double out3[3]); /* {knn s, update s, finish_iter} */
+int svnicp_set_k(svnicp_handle h, int k);
+int svnicp_set_threshold(svnicp_handle h, double max_dist);
+
+/* initialize_particles (ICPUtils.cpp:45-58) and initialize_particles_gaussian (:60-75): fills
+ * [6][P] host doubles from a counter-based RNG (seeded; torch::rand is not reproducible). */
+int svnicp_initialize_particles(int particle_count, const double ub[6], const double lb[6], uint64_t seed, double *out_6xP);
+int svnicp_initialize_particles_gaussian(int particle_count, const double cov_diag[6], uint64_t seed, double *out_6xP);
+
+/* ---- parity / debug taps (no reference counterpart; used by tests and bench only) ---- */
+int svnicp_iterations_done(svnicp_handle h, int32_t *out);
+/* candidate table of the last scan: global map indices [n_s][K], ascending (d0^2, index). */
+int svnicp_get_candidates(svnicp_handle h, int32_t *out_idx /*[n_s][K]*/, float *out_rel_xyz /*[n_s][K][3] or NULL*/);
+/* fp32 source as the kernels see it: R0*s [n_s][3] */
+int svnicp_get_source_f32(svnicp_handle h, float *out_xyz);
+/* last executed iteration (needs debug_corr): fp32 particle transforms [P_local][12] (A' row-major 9, tau 3),
+ * chosen global map index [P_local][n_s] and mask [P_local][n_s]. */
+int svnicp_get_correspondences(svnicp_handle h, float *out_transforms, int32_t *out_idx, uint8_t *out_mask);
+/* Gauss-Newton system of the last executed iteration for ALL particles: H [P][36], b [P][6], x [P][6]. */
+int svnicp_get_gn_system(svnicp_handle h, double *out_H, double *out_b, double *out_x);
+/* Stein step of the last executed iteration, local slice: delta [P_local][6]; bandwidth h. */
+int svnicp_get_stein(svnicp_handle h, double *out_delta, double *out_bandwidth);
+/* mean candidates per (point) kept by the exact pruning pass, per iteration [iterations] */
+int svnicp_get_prune_stats(svnicp_handle h, double *out_mean_kept, int32_t *rows);
+/* device time of the phases of the last scan in ms: {setup, iterations, epilogue, total} */
+int svnicp_get_timing(svnicp_handle h, double out4[4]);
+/* local particle slice [lo, hi) */
+int svnicp_get_slice(svnicp_handle h, int32_t *lo, int32_t *hi);
+/* per-phase device timing of the next scans (events around every launch group; small overhead).
+ * phase ms summed over the iterations of the last scan: {prep, filter, gn, finalize, gather, stein, setup, #iterations} */
+int svnicp_set_profiling(svnicp_handle h, int on);
+int svnicp_get_phase_times(svnicp_handle h, double out8[8]);
+/* {n_s, n_t, K, brute-force fallback queries of the candidate builder, TB, n_slices, n_pgroups, iterations enqueued} */
+int svnicp_get_scan_info(svnicp_handle h, int64_t out8[8]);
+/* number of kernel launches issued by the last svnicp_align */
+int svnicp_get_launch_count(svnicp_handle h, int64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVNICP_B200_H */

@@ -114,6 +114,38 @@ class Oracle:
             self.lib.oracle_pose_update(_ptr(R), _ptr(t), _ptr(delta), C.c_int(len(R)))
         return R, t
 
+    # ---- kernel-arithmetic mode (fp32 operation order of the CUDA kernels) ----
+    def cand_sorted(self, q0, tgt, K):
+        q0, tgt = _f64(q0), _f64(tgt)
+        idx = np.zeros((len(q0), K), dtype=np.int32)
+        rel = np.zeros((len(q0), K, 3), dtype=np.float32)
+        self.lib.oracle_cand_sorted(_ptr(q0), C.c_int64(len(q0)), _ptr(tgt), C.c_int64(len(tgt)), C.c_int(K), _ptr(idx), _ptr(rel))
+        return idx, rel
+
+    def source_f32(self, src, R0):
+        src = _f64(src)
+        sp = np.zeros((len(src), 3), dtype=np.float32)
+        self.lib.oracle_source_f32(_ptr(src), C.c_int64(len(src)), _ptr(_f64(R0)), _ptr(sp))
+        return sp
+
+    def transforms_f32(self, R, t, R0):
+        R, t = _f64(R), _f64(t)
+        xf = np.zeros((len(R), 12), dtype=np.float32)
+        self.lib.oracle_transforms_f32(_ptr(R), _ptr(t), C.c_int(len(R)), _ptr(_f64(R0)), _ptr(xf))
+        return xf
+
+    def corr_f32(self, xf, sp, rel, cidx, max_dist):
+        xf = np.ascontiguousarray(xf, dtype=np.float32)
+        sp = np.ascontiguousarray(sp, dtype=np.float32)
+        rel = np.ascontiguousarray(rel, dtype=np.float32)
+        cidx = np.ascontiguousarray(cidx, dtype=np.int32)
+        P, ns, K = len(xf), len(sp), cidx.shape[1]
+        idx = np.zeros((P, ns), dtype=np.int32)
+        mask = np.zeros((P, ns), dtype=np.uint8)
+        self.lib.oracle_corr_f32(_ptr(xf), C.c_int(P), _ptr(sp), C.c_int64(ns), _ptr(rel), _ptr(cidx), C.c_int(K),
+                                 C.c_double(max_dist), _ptr(idx), _ptr(mask))
+        return idx, mask
+
     def rbf_kernel(self, x):
         x = _f64(x)
         P = len(x)

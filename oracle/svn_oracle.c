@@ -596,3 +596,104 @@ void oracle_initialize_particles(int P, const double ub[6], const double lb[6], 
   for (int c = 0; c < 6; c++)
     for (int p = 0; p < P; p++) out[c * P + p] = (P == 1) ? 0.0 : (ub[c] - lb[c]) * u[c * P + p] + lb[c];
 }
+
+/* ========================================================================================== */
+/* Kernel-arithmetic mode: restates the fp32 operation order of the CUDA kernels so that       */
+/* correspondence indices can be compared BIT-EXACTLY "given identical transformed points"     */
+/* (BASELINE.json north_star).  Documented differences to the reference semantics:             */
+/*   - candidate slot order is ascending (d0^2, map index) instead of MinK replacement order;  */
+/*     the candidate SET is the same K nearest (fp64, same fma order);                         */
+/*   - the 1-NN runs in fp32 on coordinates RELATIVE to q0_b (c' = fp32(m - q0_b),            */
+/*     q' = A' s' + tau with A' = fp32(R0 (R_p - I) R0^T), tau = fp32(R0 t_p), s' = fp32(R0 s)); */
+/*   - tie-break: strict '<' scanning OUR slot order, i.e. among exactly equal fp32 distances  */
+/*     the candidate with the smaller (d0^2, index) wins (the reference: lower MinK slot).     */
+/* ========================================================================================== */
+
+typedef struct { double d; int64_t idx; } dist_idx;
+
+static int cmp_dist_idx(const void *a, const void *b) {
+  const dist_idx *x = (const dist_idx *)a, *y = (const dist_idx *)b;
+  if (x->d < y->d) return -1;
+  if (x->d > y->d) return 1;
+  return (x->idx > y->idx) - (x->idx < y->idx);
+}
+
+/* K nearest map points of every q0 (brute force, fp64, fma order of knn.cu:101-106), ascending
+ * (d0^2, index); padded with map point 0 when n_t < K (knn.cu:343).  rel: fp32(m - q0) [n_q][K][3]. */
+void oracle_cand_sorted(const double *q0, int64_t n_q, const double *tgt, int64_t n_t, int K,
+                        int32_t *idx_out, float *rel_out) {
+#pragma omp parallel
+  {
+    dist_idx *a = (dist_idx *)malloc(sizeof(dist_idx) * (size_t)(n_t > 0 ? n_t : 1));
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n_q; i++) {
+      const double qx = q0[3 * i], qy = q0[3 * i + 1], qz = q0[3 * i + 2];
+      for (int64_t j = 0; j < n_t; j++) {
+        double dx = qx - tgt[3 * j], dy = qy - tgt[3 * j + 1], dz = qz - tgt[3 * j + 2];
+        a[j].d = fma(dz, dz, fma(dy, dy, dx * dx));
+        a[j].idx = j;
+      }
+      qsort(a, (size_t)n_t, sizeof(dist_idx), cmp_dist_idx);
+      for (int k = 0; k < K; k++) {
+        const int64_t gi = (k < n_t) ? a[k].idx : 0;
+        idx_out[i * K + k] = (int32_t)gi;
+        if (rel_out)
+          for (int c = 0; c < 3; c++) rel_out[(i * K + k) * 3 + c] = (float)(tgt[3 * gi + c] - q0[3 * i + c]);
+      }
+    }
+    free(a);
+  }
+}
+
+/* s' = fp32(R0 s) as k_q0 computes it (fma chain without the translation). */
+void oracle_source_f32(const double *src, int64_t n_s, const double R0[9], float *sp) {
+  for (int64_t i = 0; i < n_s; i++) {
+    const double x = src[3 * i], y = src[3 * i + 1], z = src[3 * i + 2];
+    for (int r = 0; r < 3; r++) sp[3 * i + r] = (float)fma(R0[3 * r], x, fma(R0[3 * r + 1], y, R0[3 * r + 2] * z));
+  }
+}
+
+/* fp32 transforms as k_prep computes them from the fp64 particle state: xf [P][12]. */
+void oracle_transforms_f32(const double *R, const double *t, int P, const double R0[9], float *xf) {
+  for (int p = 0; p < P; p++) {
+    double D[9], T[9];
+    for (int i = 0; i < 9; i++) D[i] = R[9 * p + i] - ((i % 4 == 0) ? 1.0 : 0.0);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) T[3 * r + c] = R0[3 * r] * D[c] + R0[3 * r + 1] * D[3 + c] + R0[3 * r + 2] * D[6 + c];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++)
+        xf[12 * p + 3 * r + c] = (float)(T[3 * r] * R0[3 * c] + T[3 * r + 1] * R0[3 * c + 1] + T[3 * r + 2] * R0[3 * c + 2]);
+    for (int r = 0; r < 3; r++)
+      xf[12 * p + 9 + r] = (float)(R0[3 * r] * t[3 * p] + R0[3 * r + 1] * t[3 * p + 1] + R0[3 * r + 2] * t[3 * p + 2]);
+  }
+}
+
+/* The index-deciding arithmetic of k_gn (svn_icp_b200/csrc/iter_kernels.cu), operation by operation:
+ *   a = fmaf(A0,sx, fmaf(A1,sy, A2*sz)) ; q = a + tau ; d = fmaf(dz,dz, fmaf(dy,dy, dx*dx)) ; strict '<', first wins;
+ *   mask = d_best < (float)max_dist.   (gcc: -ffp-contract=off, fmaf() is the correctly rounded fused op)
+ * xf [P][12], sp [n_s][3], rel [n_s][K][3], cidx [n_s][K] -> idx [P][n_s], mask [P][n_s]. */
+void oracle_corr_f32(const float *xf, int P, const float *sp, int64_t n_s, const float *rel, const int32_t *cidx, int K,
+                     double max_dist, int32_t *idx_out, uint8_t *mask_out) {
+  const float Dm = (float)max_dist;
+#pragma omp parallel for schedule(static)
+  for (int p = 0; p < P; p++) {
+    const float *A = xf + 12 * p;
+    for (int64_t i = 0; i < n_s; i++) {
+      const float sx = sp[3 * i], sy = sp[3 * i + 1], sz = sp[3 * i + 2];
+      const float ax = fmaf(A[0], sx, fmaf(A[1], sy, A[2] * sz));
+      const float ay = fmaf(A[3], sx, fmaf(A[4], sy, A[5] * sz));
+      const float az = fmaf(A[6], sx, fmaf(A[7], sy, A[8] * sz));
+      const float qx = ax + A[9], qy = ay + A[10], qz = az + A[11];
+      float best = INFINITY;
+      int bi = 0;
+      for (int k = 0; k < K; k++) {
+        const float *c = rel + (i * K + k) * 3;
+        const float dx = qx - c[0], dy = qy - c[1], dz = qz - c[2];
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d < best) { best = d; bi = k; }
+      }
+      idx_out[(size_t)p * n_s + i] = cidx[i * K + bi];
+      mask_out[(size_t)p * n_s + i] = (best < Dm) ? 1 : 0;
+    }
+  }
+}

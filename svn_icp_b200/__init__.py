@@ -1,0 +1,339 @@
+"""svn_icp_b200 -- B200-native SVN-ICP registration inner loop.
+
+Python host-side mirror of the reference's registration-class interface (svnicp::SVNICP,
+reference svn-icp/include/core/SVNICP.h:29-80, SVGDICP.h:64-211) over the C ABI in
+include/svnicp_b200.h.  Same method names, argument meaning and call order
+(add_cloud -> set_initial_mean -> stein_align -> getters, OdometryPipeline.cpp:582-607).
+
+All compute happens in libsvnicp_b200.so (hand-written sm_100a CUDA).  There is no CPU fallback: if
+the library is missing or no B200 is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsvnicp_b200.so")
+
+ALIGN_SUCCESS = 1  # SteinICPState, SVGDICP.h:59-62
+NO_OPTIMIZER = 2
+CLASS_SVNICP = 0
+CLASS_SVGDICP = 1
+
+
+class SvnIcpError(RuntimeError):
+    pass
+
+
+class _CParams(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("use_minibatch", C.c_int32), ("batch_size", C.c_int32), ("lr", C.c_double),
+                ("max_dist", C.c_double), ("normalize_cloud", C.c_int32), ("optimizer", C.c_char * 16),
+                ("check_early_stop", C.c_int32), ("convergence_steps", C.c_int32), ("convergence_threshold", C.c_double),
+                ("KNN_count", C.c_int32), ("SVN_full_grad", C.c_int32), ("use_weight_mean", C.c_int32),
+                ("grid_cell", C.c_double), ("debug_corr", C.c_int32)]
+
+
+@dataclasses.dataclass
+class SteinICPParam:
+    """SteinICPParam (SVGDICP.h:41-57), same field names and defaults."""
+    iterations: int = 50
+    use_minibatch: bool = False
+    batch_size: int = 50
+    lr: float = 0.02
+    max_dist: float = 1.0
+    normalize_cloud: bool = True
+    optimizer: str = "Adam"
+    check_early_stop: bool = False
+    convergence_steps: int = 5
+    convergence_threshold: float = 1e-5
+    KNN_count: int = 100
+    SVN_full_grad: bool = True
+    # extensions
+    grid_cell: float = 0.0
+    debug_corr: bool = False
+
+
+@dataclasses.dataclass
+class ParticleWeightOpt:
+    """ParticleWeightOpt (SVNICP.h:25-27)."""
+    use_weight_mean: bool = False
+
+
+_lib = None
+
+EXPORTS = [
+    "svnicp_abi_version", "svnicp_default_params", "svnicp_create", "svnicp_destroy", "svnicp_last_error", "svnicp_set_stream",
+    "svnicp_nccl_unique_id", "svnicp_init_sharding", "svnicp_add_cloud", "svnicp_set_initial_mean", "svnicp_align",
+    "svnicp_get_transformation", "svnicp_get_distribution", "svnicp_get_cov_matrix", "svnicp_get_particles",
+    "svnicp_get_particle_weight", "svnicp_get_particle_history", "svnicp_get_runtime", "svnicp_set_k", "svnicp_set_threshold",
+    "svnicp_initialize_particles", "svnicp_initialize_particles_gaussian", "svnicp_iterations_done", "svnicp_get_candidates",
+    "svnicp_get_source_f32", "svnicp_get_correspondences", "svnicp_get_gn_system", "svnicp_get_stein", "svnicp_get_prune_stats",
+    "svnicp_get_timing", "svnicp_get_slice", "svnicp_get_launch_count", "svnicp_set_profiling", "svnicp_get_phase_times",
+    "svnicp_get_scan_info",
+]
+
+
+def load_library() -> C.CDLL:
+    """dlopen the product library; raise loudly when it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SvnIcpError(f"{LIB_PATH} not found: build it with `python -m svn_icp_b200.build` "
+                              "(there is no CPU or PyTorch fallback for this path)")
+        lib = C.CDLL(LIB_PATH)
+        lib.svnicp_last_error.restype = C.c_char_p
+        lib.svnicp_last_error.argtypes = [C.c_void_p]
+        for name in EXPORTS:
+            fn = getattr(lib, name)
+            if name not in ("svnicp_last_error", "svnicp_destroy", "svnicp_default_params"):
+                fn.restype = C.c_int
+        lib.svnicp_destroy.restype = None
+        lib.svnicp_destroy.argtypes = [C.c_void_p]
+        lib.svnicp_default_params.restype = None
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def initialize_particles(particle_count: int, ub, lb, seed: int = 0) -> np.ndarray:
+    """initialize_particles (ICPUtils.cpp:45-58) -> [6, P]."""
+    out = np.zeros((6, particle_count))
+    rc = load_library().svnicp_initialize_particles(C.c_int(particle_count), _p(_f64(ub)), _p(_f64(lb)), C.c_uint64(seed), _p(out))
+    if rc:
+        raise SvnIcpError("initialize_particles: invalid argument")
+    return out
+
+
+def initialize_particles_gaussian(particle_count: int, cov_diag, seed: int = 0) -> np.ndarray:
+    """initialize_particles_gaussian (ICPUtils.cpp:60-75) -> [6, P]."""
+    out = np.zeros((6, particle_count))
+    rc = load_library().svnicp_initialize_particles_gaussian(C.c_int(particle_count), _p(_f64(cov_diag)), C.c_uint64(seed), _p(out))
+    if rc:
+        raise SvnIcpError("initialize_particles_gaussian: invalid argument")
+    return out
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = load_library().svnicp_nccl_unique_id(buf)
+    if rc:
+        raise SvnIcpError("ncclGetUniqueId failed: " + (load_library().svnicp_last_error(None) or b"").decode())
+    return buf.raw
+
+
+class SVNICP:
+    """Drop-in for svnicp::SVNICP.  init_pose: [6, P] (or the reference's [6, P, 1])."""
+
+    class_type = CLASS_SVNICP
+
+    def __init__(self, param: SteinICPParam, init_pose, opt: ParticleWeightOpt | None = None, device: int = -1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        init_pose = _f64(init_pose).reshape(6, -1)
+        self.particle_size = init_pose.shape[1]
+        self.param = dataclasses.replace(param)
+        cp = _CParams()
+        self._lib.svnicp_default_params(C.byref(cp))
+        for f in ("iterations", "batch_size", "convergence_steps", "KNN_count"):
+            setattr(cp, f, int(getattr(param, f)))
+        for f in ("use_minibatch", "normalize_cloud", "check_early_stop", "SVN_full_grad", "debug_corr"):
+            setattr(cp, f, int(bool(getattr(param, f))))
+        for f in ("lr", "max_dist", "convergence_threshold", "grid_cell"):
+            setattr(cp, f, float(getattr(param, f)))
+        cp.optimizer = param.optimizer.encode()[:15]
+        cp.use_weight_mean = int(bool(opt.use_weight_mean)) if opt else 0
+        rc = self._lib.svnicp_create(C.byref(self._h), C.byref(cp), C.c_int(self.particle_size), _p(init_pose),
+                                     C.c_int(self.class_type), C.c_int(device))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise SvnIcpError(f"svnicp_create failed ({rc}): " + (self._lib.svnicp_last_error(None) or b"").decode())
+        self.n_s = 0
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc < 0:
+            raise SvnIcpError(f"{what} failed ({rc}): " + (self._lib.svnicp_last_error(self._h) or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.svnicp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.svnicp_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
+
+    def init_sharding(self, unique_id: bytes, rank: int, n_ranks: int):
+        self._check(self._lib.svnicp_init_sharding(self._h, C.c_char_p(unique_id), C.c_int(rank), C.c_int(n_ranks)), "init_sharding")
+
+    # -- the reference interface ------------------------------------------------------------------
+    def add_cloud(self, source, target, init_pose):
+        """SVGDICP::add_cloud (SVGDICP.cpp:46-62).  source/target: host arrays [N,3] float64."""
+        source, target = _f64(source), _f64(target)
+        init_pose = _f64(init_pose).reshape(6, -1)
+        if init_pose.shape[1] != self.particle_size:
+            raise SvnIcpError("add_cloud: particle count is fixed at construction (SVNICP.cpp:42,167)")
+        self.n_s = len(source)
+        self._check(self._lib.svnicp_add_cloud(self._h, _p(source), C.c_int64(len(source)), C.c_int(0), _p(target),
+                                               C.c_int64(len(target)), C.c_int(0), _p(init_pose)), "add_cloud")
+
+    def add_cloud_device(self, source_ptr: int, n_s: int, target_ptr: int, n_t: int, init_pose):
+        """Same, with the clouds already resident in HBM (float64 [N,3] device pointers), as in the reference where
+        the caller uploads (OdometryPipeline.cpp:574,581)."""
+        init_pose = _f64(init_pose).reshape(6, -1)
+        self.n_s = n_s
+        self._check(self._lib.svnicp_add_cloud(self._h, C.c_void_p(source_ptr), C.c_int64(n_s), C.c_int(1), C.c_void_p(target_ptr),
+                                               C.c_int64(n_t), C.c_int(1), _p(init_pose)), "add_cloud")
+
+    def add_cloud_pinned(self, source_ptr: int, n_s: int, target_ptr: int, n_t: int, init_pose):
+        """Same, host pointers given as integers (e.g. pinned torch tensors' data_ptr())."""
+        init_pose = _f64(init_pose).reshape(6, -1)
+        self.n_s = n_s
+        self._check(self._lib.svnicp_add_cloud(self._h, C.c_void_p(source_ptr), C.c_int64(n_s), C.c_int(0), C.c_void_p(target_ptr),
+                                               C.c_int64(n_t), C.c_int(0), _p(init_pose)), "add_cloud")
+
+    def set_initial_mean(self, R0, t0):
+        """SVGDICP::set_initial_mean (SVGDICP.h:102-110): rotation matrix [3,3] and translation [3] of the guess."""
+        self._check(self._lib.svnicp_set_initial_mean(self._h, _p(_f64(R0).reshape(9)), _p(_f64(t0).reshape(3))), "set_initial_mean")
+
+    def stein_align(self) -> int:
+        """SVNICP::stein_align (SVNICP.cpp:41-114) -> SteinICPState."""
+        return self._check(self._lib.svnicp_align(self._h), "stein_align")
+
+    def get_transformation(self) -> np.ndarray:
+        out = np.zeros(6)
+        self._check(self._lib.svnicp_get_transformation(self._h, _p(out)), "get_transformation")
+        return out
+
+    def get_distribution(self) -> np.ndarray:
+        out = np.zeros(6)
+        self._check(self._lib.svnicp_get_distribution(self._h, _p(out)), "get_distribution")
+        return out
+
+    def get_cov_matrix(self) -> np.ndarray:
+        out = np.zeros(36)
+        self._check(self._lib.svnicp_get_cov_matrix(self._h, _p(out)), "get_cov_matrix")
+        return out
+
+    def get_particles(self) -> np.ndarray:
+        """6P doubles, component-major [6][P] (SVGDICP.cpp:515-520)."""
+        out = np.zeros(6 * self.particle_size)
+        self._check(self._lib.svnicp_get_particles(self._h, _p(out)), "get_particles")
+        return out
+
+    def get_particle_weight(self) -> np.ndarray:
+        out = np.zeros(self.particle_size)
+        self._check(self._lib.svnicp_get_particle_weight(self._h, _p(out)), "get_particle_weight")
+        return out
+
+    def get_particle_history(self) -> np.ndarray:
+        """[iterations, 6P] float32 (SVGDICP.cpp:526-534)."""
+        I = self.param.iterations
+        out = np.zeros((max(I, 1), 6 * self.particle_size), dtype=np.float32)
+        rows = C.c_int32(0)
+        self._check(self._lib.svnicp_get_particle_history(self._h, _p(out), C.byref(rows)), "get_particle_history")
+        return out[:I]
+
+    def get_runtime(self) -> np.ndarray:
+        out = np.zeros(3)
+        self._check(self._lib.svnicp_get_runtime(self._h, _p(out)), "get_runtime")
+        return out
+
+    def set_k(self, k: int):
+        self._check(self._lib.svnicp_set_k(self._h, C.c_int(k)), "set_k")
+        self.param.KNN_count = k
+
+    def set_threshold(self, max_dist: float):
+        self._check(self._lib.svnicp_set_threshold(self._h, C.c_double(max_dist)), "set_threshold")
+
+    # -- parity / debug taps ----------------------------------------------------------------------
+    def iterations_done(self) -> int:
+        v = C.c_int32(0)
+        self._check(self._lib.svnicp_iterations_done(self._h, C.byref(v)), "iterations_done")
+        return v.value
+
+    def slice(self):
+        lo, hi = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.svnicp_get_slice(self._h, C.byref(lo), C.byref(hi)), "get_slice")
+        return lo.value, hi.value
+
+    def get_candidates(self, want_rel=False):
+        K = self.param.KNN_count
+        idx = np.zeros((self.n_s, K), dtype=np.int32)
+        rel = np.zeros((self.n_s, K, 3), dtype=np.float32) if want_rel else None
+        self._check(self._lib.svnicp_get_candidates(self._h, _p(idx), _p(rel)), "get_candidates")
+        return (idx, rel) if want_rel else idx
+
+    def get_source_f32(self):
+        out = np.zeros((self.n_s, 3), dtype=np.float32)
+        self._check(self._lib.svnicp_get_source_f32(self._h, _p(out)), "get_source_f32")
+        return out
+
+    def get_correspondences(self):
+        lo, hi = self.slice()
+        xf = np.zeros((hi - lo, 12), dtype=np.float32)
+        idx = np.zeros((hi - lo, self.n_s), dtype=np.int32)
+        mask = np.zeros((hi - lo, self.n_s), dtype=np.uint8)
+        self._check(self._lib.svnicp_get_correspondences(self._h, _p(xf), _p(idx), _p(mask)), "get_correspondences")
+        return xf, idx, mask
+
+    def get_gn_system(self):
+        P = self.particle_size
+        H, b, x = np.zeros((P, 6, 6)), np.zeros((P, 6)), np.zeros((P, 6))
+        self._check(self._lib.svnicp_get_gn_system(self._h, _p(H), _p(b), _p(x)), "get_gn_system")
+        return H, b, x
+
+    def get_stein(self):
+        lo, hi = self.slice()
+        d = np.zeros((hi - lo, 6))
+        h = C.c_double(0)
+        self._check(self._lib.svnicp_get_stein(self._h, _p(d), C.byref(h)), "get_stein")
+        return d, h.value
+
+    def get_prune_stats(self):
+        out = np.zeros(max(self.param.iterations, 1))
+        rows = C.c_int32(0)
+        self._check(self._lib.svnicp_get_prune_stats(self._h, _p(out), C.byref(rows)), "get_prune_stats")
+        return out[:self.param.iterations]
+
+    def get_timing(self):
+        out = np.zeros(4)
+        self._check(self._lib.svnicp_get_timing(self._h, _p(out)), "get_timing")
+        return dict(setup_ms=out[0], iterations_ms=out[1], epilogue_ms=out[2], total_ms=out[3])
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.svnicp_set_profiling(self._h, C.c_int(int(on))), "set_profiling")
+
+    def get_phase_times(self):
+        out = np.zeros(8)
+        self._check(self._lib.svnicp_get_phase_times(self._h, _p(out)), "get_phase_times")
+        names = ["prep_ms", "filter_ms", "gn_ms", "finalize_ms", "gather_ms", "stein_ms", "setup_ms", "iterations"]
+        return dict(zip(names, out.tolist()))
+
+    def get_scan_info(self):
+        out = np.zeros(8, dtype=np.int64)
+        self._check(self._lib.svnicp_get_scan_info(self._h, _p(out)), "get_scan_info")
+        names = ["n_s", "n_t", "K", "knn_fallback_queries", "TB", "n_slices", "n_pgroups", "iterations_enqueued"]
+        return dict(zip(names, out.tolist()))
+
+    def launch_count(self) -> int:
+        v = C.c_int64(0)
+        self._check(self._lib.svnicp_get_launch_count(self._h, C.byref(v)), "get_launch_count")
+        return v.value

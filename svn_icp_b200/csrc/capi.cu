@@ -1,0 +1,780 @@
+// capi.cu -- the C ABI (include/svnicp_b200.h) and the host-side scan driver.
+//
+// Host logic mirrors the call order the reference's caller uses (OdometryPipeline.cpp:582-607):
+// add_cloud -> set_initial_mean -> stein_align -> getters.  Everything heavy is a kernel launch on one
+// CUDA stream; the host only sequences launches, one ncclAllGather per iteration when sharded, and one
+// small device->host copy at the end of the scan.  No CPU compute path exists.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/svnicp_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace svn;
+
+static thread_local std::string g_create_error;
+
+// ---- NCCL through dlopen (no link-time dependency; torch's bundled libnccl is reused when loaded) ----
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string &err) {
+    if (lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy || !GetErrorString) { err = "libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n, bool zero = false) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    cap = want;
+    if (zero) e = cudaMemset(p, 0, want * sizeof(T));
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct svnicp_handle_t {
+  svnicp_params prm;
+  int class_type = 0;
+  int device = 0;
+  int sm_count = 148;
+  int P = 0, p_lo = 0, P_l = 0, P_pad = 0, P_l_max = 0;
+  int rank = 0, n_ranks = 1;
+  ncclComm_t comm = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  int K = 100;
+  double max_dist = 1.0;
+  // scan inputs
+  int64_t n_s = 0, n_t = 0;
+  int n_pad = 0;
+  bool have_cloud = false, aligned = false;
+  ScanConst sc;
+  // device buffers
+  DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, rec, xs, delta, Hbar_inv, stats, particles, init_pose;
+  DevBuf<float4> sp, cand, clist;
+  DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc;  // misc: [0] cursor, [1] fallback count
+  DevBuf<unsigned long long> keys, kept_hist;
+  DevBuf<float> xf, history;
+  DevBuf<unsigned> hist;
+  DevBuf<Ctrl> ctrl;
+  DevBuf<int32_t> dbg_idx;
+  DevBuf<uint8_t> dbg_mask;
+  // pinned host mirrors
+  double *h_stats = nullptr;      // 48
+  double *h_particles = nullptr;  // 6P
+  float *h_history = nullptr;     // I*6*P
+  Ctrl *h_ctrl = nullptr;
+  int *h_stop = nullptr;          // per-iteration stop snapshots
+  unsigned long long *h_kept = nullptr;
+  size_t h_hist_cap = 0, h_stop_cap = 0;
+  std::vector<cudaEvent_t> iter_events;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // results
+  int iters_done = 0;
+  int enqueued_iters = 0;
+  double ms_setup = 0, ms_iter = 0, ms_epi = 0, ms_total = 0;
+  int64_t launches = 0;
+  int fallback_queries = 0;
+  // optional per-phase device timing (svnicp_set_profiling): events around every launch group
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_events;  // 7 per iteration
+  double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // prep, filter, gn, finalize, gather, stein(decide+median+stein+update), setup, iterations executed
+  // launch shape
+  int TB = 16, stages = 3, n_slices = 1, n_pgroups = 1, PG = 256, RG = 1;
+  size_t gn_smem = 0;
+};
+
+static int fail(svnicp_handle h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess)                                                                                   \
+      return fail(h, e__ == cudaErrorMemoryAllocation ? SVNICP_ERR_OOM : SVNICP_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                               \
+  } while (0)
+
+#define NC(call)                                                                                         \
+  do {                                                                                                   \
+    ncclResult_t r__ = (call);                                                                           \
+    if (r__ != ncclSuccess) return fail(h, SVNICP_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r__)); \
+  } while (0)
+
+extern "C" {
+
+int svnicp_abi_version(void) { return SVNICP_B200_ABI_VERSION; }
+
+void svnicp_default_params(svnicp_params *p) {
+  memset(p, 0, sizeof(*p));
+  p->iterations = 50;
+  p->use_minibatch = 0;
+  p->batch_size = 50;
+  p->lr = 0.02;
+  p->max_dist = 1.0;
+  p->normalize_cloud = 1;
+  strcpy(p->optimizer, "Adam");
+  p->check_early_stop = 0;
+  p->convergence_steps = 5;
+  p->convergence_threshold = 1e-5;
+  p->KNN_count = 100;
+  p->SVN_full_grad = 1;
+  p->use_weight_mean = 0;
+  p->grid_cell = 0.0;
+  p->debug_corr = 0;
+}
+
+const char *svnicp_last_error(svnicp_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static void set_slice(svnicp_handle h) {
+  h->P_l_max = (h->P + h->n_ranks - 1) / h->n_ranks;
+  h->P_pad = h->P_l_max * h->n_ranks;
+  h->p_lo = h->rank * h->P_l_max;
+  int hi = h->p_lo + h->P_l_max;
+  if (hi > h->P) hi = h->P;
+  h->P_l = hi > h->p_lo ? hi - h->p_lo : 0;
+}
+
+static int upload_particles(svnicp_handle h, const double *init_pose) {
+  const size_t n = (size_t)6 * h->P;
+  CU(h->init_pose.ensure(n));
+  if (init_pose) CU(cudaMemcpyAsync(h->init_pose.p, init_pose, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  else CU(cudaMemsetAsync(h->init_pose.p, 0, n * sizeof(double), h->stream));
+  launch_init_particles(h->R.p, h->t.p, h->init_pose.p, h->P, h->dnorm.p, h->p_lo, h->P_l, h->ctrl.p, h->stream);
+  CU(cudaGetLastError());
+  // the copy source is caller memory: finish before returning (the reference clones synchronously too)
+  CU(cudaStreamSynchronize(h->stream));
+  return SVNICP_OK;
+}
+
+static int alloc_particle_state(svnicp_handle h) {
+  const size_t P = (size_t)h->P_pad;
+  CU(h->R.ensure(9 * P, true));
+  CU(h->t.ensure(3 * P, true));
+  CU(h->dnorm.ensure(P, true));
+  CU(h->rec.ensure(P * REC, true));
+  CU(h->xs.ensure(6 * P));
+  CU(h->delta.ensure(6 * P, true));
+  CU(h->Hbar_inv.ensure(36));
+  CU(h->stats.ensure(48));
+  CU(h->particles.ensure(6 * P));
+  CU(h->xf.ensure(12 * P));
+  CU(h->hist.ensure((size_t)MED_PASSES * MED_BINS));
+  CU(h->ctrl.ensure(1, true));
+  CU(h->misc.ensure(8, true));
+  const size_t I = (size_t)(h->prm.iterations > 0 ? h->prm.iterations : 1);
+  CU(h->history.ensure(I * 6 * h->P));
+  CU(h->kept_hist.ensure(I + 2, true));
+  return SVNICP_OK;
+}
+
+int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_count, const double *init_pose, int class_type,
+                  int device) {
+  if (!out || !params) return fail(nullptr, SVNICP_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (particle_count < 1) return fail(nullptr, SVNICP_ERR_INVALID, "particle_count must be >= 1");
+  if (class_type != SVNICP_CLASS_SVNICP)
+    return fail(nullptr, SVNICP_ERR_INVALID, "class_type SVGDICP (first-order path, SURVEY.md 8(f) row 2) is not built yet");
+  if (params->KNN_count < 1 || params->KNN_count > 256) return fail(nullptr, SVNICP_ERR_INVALID, "KNN_count must be in [1,256]");
+  if (params->iterations < 0) return fail(nullptr, SVNICP_ERR_INVALID, "iterations must be >= 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, SVNICP_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (device < 0) cudaGetDevice(&device);
+  if (device >= ndev) return fail(nullptr, SVNICP_ERR_NO_DEVICE, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, SVNICP_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(nullptr, SVNICP_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+  svnicp_handle h = new svnicp_handle_t();
+  h->prm = *params;
+  h->class_type = class_type;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->P = particle_count;
+  h->K = params->KNN_count;
+  h->max_dist = params->max_dist;
+  memset(&h->sc, 0, sizeof(h->sc));
+  h->sc.R0[0] = h->sc.R0[4] = h->sc.R0[8] = 1.0;  // SVGDICP.cpp:38-39
+  set_slice(h);
+  int rc = SVNICP_OK;
+  auto body = [&]() -> int {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    for (int i = 0; i < 4; i++) CU(cudaEventCreate(&h->ev[i]));
+    init_iter_kernels();
+    CU(cudaGetLastError());
+    int r = alloc_particle_state(h);
+    if (r) return r;
+    CU(cudaMallocHost((void **)&h->h_stats, 48 * sizeof(double)));
+    CU(cudaMallocHost((void **)&h->h_particles, (size_t)6 * h->P * sizeof(double)));
+    CU(cudaMallocHost((void **)&h->h_ctrl, sizeof(Ctrl)));
+    memset(h->h_stats, 0, 48 * sizeof(double));
+    memset(h->h_particles, 0, (size_t)6 * h->P * sizeof(double));
+    return upload_particles(h, init_pose);
+  };
+  rc = body();
+  if (rc != SVNICP_OK) {
+    g_create_error = h->err;
+    svnicp_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return SVNICP_OK;
+}
+
+void svnicp_destroy(svnicp_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  DevBuf<double> *d[] = {&h->src64, &h->tgt64, &h->q0, &h->sxyz, &h->R, &h->t, &h->dnorm, &h->part, &h->rec, &h->xs, &h->delta,
+                         &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose};
+  for (auto *b : d) b->release();
+  h->sp.release(); h->cand.release(); h->clist.release();
+  h->ccount.release(); h->counts.release(); h->starts.release(); h->fill.release(); h->pt_slot.release(); h->sidx.release(); h->misc.release();
+  h->keys.release(); h->kept_hist.release(); h->xf.release(); h->history.release(); h->hist.release(); h->ctrl.release();
+  h->dbg_idx.release(); h->dbg_mask.release();
+  if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->h_particles) cudaFreeHost(h->h_particles);
+  if (h->h_history) cudaFreeHost(h->h_history);
+  if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  if (h->h_stop) cudaFreeHost(h->h_stop);
+  if (h->h_kept) cudaFreeHost(h->h_kept);
+  for (auto e : h->iter_events) cudaEventDestroy(e);
+  for (auto e : h->prof_events) cudaEventDestroy(e);
+  for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int svnicp_set_stream(svnicp_handle h, void *cuda_stream) {
+  if (!h) return SVNICP_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return SVNICP_OK;
+}
+
+int svnicp_nccl_unique_id(void *id128) {
+  std::string err;
+  if (!id128) return SVNICP_ERR_INVALID;
+  if (!g_nccl.load(err)) return fail(nullptr, SVNICP_ERR_NCCL, "%s", err.c_str());
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, SVNICP_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(id128, &id, 128);
+  return SVNICP_OK;
+}
+
+int svnicp_init_sharding(svnicp_handle h, const void *unique_id128, int rank, int n_ranks) {
+  if (!h || !unique_id128) return SVNICP_ERR_INVALID;
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, SVNICP_ERR_INVALID, "bad rank %d / %d", rank, n_ranks);
+  if (h->P < n_ranks) return fail(h, SVNICP_ERR_INVALID, "need at least one particle per rank (P=%d, ranks=%d)", h->P, n_ranks);
+  if (h->comm) return fail(h, SVNICP_ERR_INVALID, "sharding already initialised");
+  CU(cudaSetDevice(h->device));
+  if (n_ranks > 1) {
+    std::string err;
+    if (!g_nccl.load(err)) return fail(h, SVNICP_ERR_NCCL, "%s", err.c_str());
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, 128);
+    NC(g_nccl.CommInitRank(&h->comm, n_ranks, id, rank));
+  }
+  h->rank = rank;
+  h->n_ranks = n_ranks;
+  set_slice(h);
+  if ((h->P_l_max * n_ranks - h->P) >= h->P_l_max) return fail(h, SVNICP_ERR_INVALID, "P=%d leaves a rank without particles", h->P);
+  int r = alloc_particle_state(h);
+  if (r) return r;
+  h->have_cloud = false;
+  return SVNICP_OK;
+}
+
+static int choose_shape(svnicp_handle h) {
+  const int K = h->K;
+  int TB = 32;
+  const int S = 3;
+  while (TB > 4 && gn_stage_bytes(TB, K) * S > 100 * 1024) TB >>= 1;
+  h->TB = TB;
+  h->stages = S;
+  h->gn_smem = gn_stage_bytes(TB, K) * S + 2 * S * sizeof(uint64_t) + 128;
+  int PG = 1;
+  while (PG < h->P_l && PG < 256) PG <<= 1;
+  h->PG = PG;
+  h->RG = 256 / PG;
+  h->n_pgroups = (h->P_l + PG - 1) / PG;
+  if (h->n_pgroups < 1) h->n_pgroups = 1;
+  return SVNICP_OK;
+}
+
+int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int source_on_device, const double *target, int64_t n_t,
+                     int target_on_device, const double *init_pose) {
+  if (!h) return SVNICP_ERR_INVALID;
+  if (!source || !target || n_s < 1 || n_t < 1) return fail(h, SVNICP_ERR_INVALID, "add_cloud: empty cloud (n_s=%lld, n_t=%lld)", (long long)n_s, (long long)n_t);
+  if (n_s > (1ll << 30) || n_t > (1ll << 30)) return fail(h, SVNICP_ERR_INVALID, "add_cloud: cloud too large");
+  CU(cudaSetDevice(h->device));
+  choose_shape(h);
+  const int TB = h->TB;
+  const int n_pad = (int)(((n_s + TB - 1) / TB) * TB);
+  CU(h->src64.ensure((size_t)3 * n_s));
+  CU(h->tgt64.ensure((size_t)3 * n_t));
+  CU(cudaMemcpyAsync(h->src64.p, source, (size_t)3 * n_s * sizeof(double), source_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->tgt64.p, target, (size_t)3 * n_t * sizeof(double), target_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  h->n_s = n_s;
+  h->n_t = n_t;
+  h->n_pad = n_pad;
+  CU(h->q0.ensure((size_t)3 * n_s));
+  CU(h->sp.ensure((size_t)n_pad + 64));
+  CU(h->cand.ensure((size_t)n_s * h->K));
+  CU(h->clist.ensure((size_t)n_pad * h->K));
+  CU(h->ccount.ensure((size_t)n_pad + 64));
+  CU(cudaMemsetAsync(h->ccount.p, 0, ((size_t)n_pad + 64) * sizeof(int), h->stream));
+  size_t table = 1024;
+  while (table < (size_t)2 * n_t) table <<= 1;
+  CU(h->keys.ensure(table));
+  CU(h->counts.ensure(table));
+  CU(h->starts.ensure(table));
+  CU(h->fill.ensure(table));
+  CU(h->pt_slot.ensure((size_t)n_t));
+  CU(h->sidx.ensure((size_t)n_t));
+  CU(h->sxyz.ensure((size_t)3 * n_t));
+  const int n_tiles = n_pad / TB;
+  int n_slices = (2 * h->sm_count) / h->n_pgroups;
+  if (n_slices < 1) n_slices = 1;
+  if (n_slices > n_tiles) n_slices = n_tiles;
+  h->n_slices = n_slices;
+  CU(h->part.ensure((size_t)n_slices * h->RG * (h->P_l > 0 ? h->P_l : 1) * NACC));
+  if (h->prm.debug_corr) {
+    CU(h->dbg_idx.ensure((size_t)h->P_l * n_s));
+    CU(h->dbg_mask.ensure((size_t)h->P_l * n_s));
+  }
+  h->have_cloud = true;
+  h->aligned = false;
+  return upload_particles(h, init_pose);  // SVGDICP.cpp:47-61 (also synchronises the cloud copies)
+}
+
+int svnicp_set_initial_mean(svnicp_handle h, const double R0[9], const double t0[3]) {
+  if (!h || !R0 || !t0) return SVNICP_ERR_INVALID;
+  memcpy(h->sc.R0, R0, 9 * sizeof(double));
+  memcpy(h->sc.t0, t0, 3 * sizeof(double));
+  return SVNICP_OK;
+}
+
+int svnicp_set_k(svnicp_handle h, int k) {
+  if (!h) return SVNICP_ERR_INVALID;
+  if (k < 1 || k > 256) return fail(h, SVNICP_ERR_INVALID, "set_k: K must be in [1,256]");
+  h->K = k;            // SVGDICP.h:98; takes effect at the next add_cloud (buffers are sized there)
+  h->have_cloud = false;
+  return SVNICP_OK;
+}
+
+int svnicp_set_threshold(svnicp_handle h, double max_dist) {
+  if (!h) return SVNICP_ERR_INVALID;
+  h->max_dist = max_dist;  // SVGDICP.h:100
+  return SVNICP_OK;
+}
+
+static int do_allgather(svnicp_handle h) {
+  if (h->n_ranks <= 1) return SVNICP_OK;
+  // in place: this rank's block already sits at rec + p_lo*REC
+  NC(g_nccl.AllGather(h->rec.p + (size_t)h->p_lo * REC, h->rec.p, (size_t)h->P_l_max * REC, ncclDouble, h->comm, h->stream));
+  return SVNICP_OK;
+}
+
+int svnicp_align(svnicp_handle h) {
+  if (!h) return SVNICP_ERR_INVALID;
+  if (!h->have_cloud) return fail(h, SVNICP_ERR_INVALID, "stein_align before add_cloud");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int I = h->prm.iterations;
+  h->launches = 0;
+  // host mirrors sized for this run
+  if (h->h_hist_cap < (size_t)(I > 0 ? I : 1) * 6 * h->P) {
+    if (h->h_history) cudaFreeHost(h->h_history);
+    h->h_hist_cap = (size_t)(I > 0 ? I : 1) * 6 * h->P;
+    CU(cudaMallocHost((void **)&h->h_history, h->h_hist_cap * sizeof(float)));
+  }
+  if (h->h_stop_cap < (size_t)I + 4) {
+    if (h->h_stop) cudaFreeHost(h->h_stop);
+    if (h->h_kept) cudaFreeHost(h->h_kept);
+    h->h_stop_cap = (size_t)I + 4;
+    CU(cudaMallocHost((void **)&h->h_stop, h->h_stop_cap * sizeof(int)));
+    CU(cudaMallocHost((void **)&h->h_kept, h->h_stop_cap * sizeof(unsigned long long)));
+  }
+  while ((int)h->iter_events.size() < I + 1) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->iter_events.push_back(e);
+  }
+  CU(h->history.ensure((size_t)(I > 0 ? I : 1) * 6 * h->P));
+  CU(h->kept_hist.ensure((size_t)I + 2, true));
+  CU(cudaMemsetAsync(h->history.p, 0, (size_t)(I > 0 ? I : 1) * 6 * h->P * sizeof(float), st));  // SVGDICP.cpp:172-174
+  CU(cudaMemsetAsync(h->kept_hist.p, 0, ((size_t)I + 2) * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(h->misc.p, 0, 8 * sizeof(int), st));
+
+  CU(cudaEventRecord(h->ev[0], st));
+  // ---- per-scan setup: candidate table (SVGDICP.cpp:176-215) ----
+  CandBuildArgs cb;
+  cb.src64 = h->src64.p; cb.tgt64 = h->tgt64.p;
+  cb.n_s = (int)h->n_s; cb.n_pad = h->n_pad; cb.n_t = (int)h->n_t; cb.K = h->K;
+  cb.sc = h->sc;
+  cb.cell = h->prm.grid_cell > 0 ? h->prm.grid_cell : 1.5;
+  cb.q0 = h->q0.p; cb.sp = h->sp.p;
+  cb.keys = h->keys.p; cb.counts = h->counts.p; cb.starts = h->starts.p; cb.fill = h->fill.p; cb.pt_slot = h->pt_slot.p;
+  cb.cursor = h->misc.p; cb.fallback_count = h->misc.p + 1;
+  size_t table = 1024;
+  while (table < (size_t)2 * h->n_t) table <<= 1;
+  cb.table_size = (int)table;
+  cb.sxyz = h->sxyz.p; cb.sidx = h->sidx.p; cb.cand = h->cand.p;
+  cb.sm_count = h->sm_count;
+  h->launches += launch_cand_build(cb, st);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev[1], st));
+
+  IterArgs ia;
+  memset(&ia, 0, sizeof(ia));
+  ia.n_s = (int)h->n_s; ia.n_pad = h->n_pad; ia.K = h->K;
+  ia.P = h->P; ia.p_lo = h->p_lo; ia.P_l = h->P_l;
+  ia.sc = h->sc;
+  ia.max_dist = (float)h->max_dist;
+  ia.sp = h->sp.p; ia.cand = h->cand.p; ia.clist = h->clist.p; ia.ccount = h->ccount.p;
+  ia.R = h->R.p; ia.t = h->t.p; ia.xf = h->xf.p; ia.dnorm = h->dnorm.p; ia.part = h->part.p; ia.rec = h->rec.p; ia.ctrl = h->ctrl.p;
+  ia.TB = h->TB; ia.stages = h->stages; ia.n_slices = h->n_slices; ia.n_pgroups = h->n_pgroups; ia.PG = h->PG; ia.RG = h->RG;
+  ia.gn_smem = h->gn_smem; ia.sm_count = h->sm_count; ia.svn_full_grad = h->prm.SVN_full_grad;
+  ia.dbg_idx = h->prm.debug_corr ? h->dbg_idx.p : nullptr;
+  ia.dbg_mask = h->prm.debug_corr ? h->dbg_mask.p : nullptr;
+
+  SteinArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.P = h->P; sa.p_lo = h->p_lo; sa.P_l = h->P_l; sa.I = I;
+  sa.svn_full_grad = h->prm.SVN_full_grad; sa.check_early_stop = h->prm.check_early_stop;
+  sa.lr = h->prm.lr; sa.threshold = h->prm.convergence_threshold;
+  sa.rec = h->rec.p; sa.xs = h->xs.p; sa.delta = h->delta.p; sa.dnorm = h->dnorm.p; sa.R = h->R.p; sa.t = h->t.p;
+  sa.Hbar_inv = h->Hbar_inv.p; sa.hist = h->hist.p; sa.history = h->history.p; sa.ctrl = h->ctrl.p;
+  sa.stats = h->stats.p; sa.particles = h->particles.p; sa.sm_count = h->sm_count;
+  sa.kept_hist = h->kept_hist.p;
+
+  if (h->profile)
+    while (h->prof_events.size() < (size_t)I * 7) {
+      cudaEvent_t pe;
+      CU(cudaEventCreate(&pe));
+      h->prof_events.push_back(pe);
+    }
+  // ---- iterations (SVNICP.cpp:52-108) ----
+  const int LAG = 3;
+  int e = 0;
+  for (; e < I; e++) {
+    if (h->prm.check_early_stop && e >= LAG) {
+      // deterministic host cut: the stop flag as of the END of iteration e-LAG decides (identical on every rank)
+      CU(cudaEventSynchronize(h->iter_events[e - LAG]));
+      if (h->h_stop[e - LAG]) break;
+    }
+#define PROF(k) do { if (h->profile) CU(cudaEventRecord(h->prof_events[(size_t)e * 7 + (k)], st)); } while (0)
+    PROF(0);
+    h->launches += launch_prep(ia, st);
+    PROF(1);
+    h->launches += launch_filter(ia, st);
+    PROF(2);
+    h->launches += launch_gn(ia, st);
+    PROF(3);
+    h->launches += launch_finalize(ia, st);
+    PROF(4);
+    int rc = do_allgather(h);
+    if (rc) return rc;
+    PROF(5);
+    h->launches += launch_decide(sa, st, 0);
+    h->launches += launch_median(sa, st);
+    h->launches += launch_stein(sa, st);
+    h->launches += launch_update(sa, st);
+    PROF(6);
+#undef PROF
+    CU(cudaGetLastError());
+    if (h->prm.check_early_stop) {
+      CU(cudaMemcpyAsync(&h->h_stop[e], &h->ctrl.p->stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CU(cudaEventRecord(h->iter_events[e], st));
+    }
+  }
+  h->enqueued_iters = e;
+  CU(cudaEventRecord(h->ev[2], st));
+  // ---- epilogue: final x, last stop decision / history row, getters (SVNICP.cpp:111, :281-308) ----
+  h->launches += launch_prep(ia, st);
+  {
+    int rc = do_allgather(h);
+    if (rc) return rc;
+  }
+  h->launches += launch_decide(sa, st, 1);
+  h->launches += launch_stats(sa, st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h->h_stats, h->stats.p, 48 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_particles, h->particles.p, (size_t)6 * h->P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_ctrl, h->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_kept, h->kept_hist.p, ((size_t)I + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(h->ev[3], st));
+  CU(cudaStreamSynchronize(st));
+  h->iters_done = h->h_ctrl->iters_done;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->ms_setup = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->ms_iter = ms;
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->ms_epi = ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->ms_total = ms;
+  if (h->profile) {
+    for (int k = 0; k < 8; k++) h->phase_ms[k] = 0;
+    for (int it = 0; it < h->enqueued_iters; it++)
+      for (int k = 0; k < 6; k++) {
+        cudaEventElapsedTime(&ms, h->prof_events[(size_t)it * 7 + k], h->prof_events[(size_t)it * 7 + k + 1]);
+        h->phase_ms[k] += ms;
+      }
+    h->phase_ms[6] = h->ms_setup;
+    h->phase_ms[7] = (double)h->enqueued_iters;
+  }
+  int misc[2] = {0, 0};
+  CU(cudaMemcpy(misc, h->misc.p, sizeof(misc), cudaMemcpyDeviceToHost));
+  h->fallback_queries = misc[1];
+  h->aligned = true;
+  return SVNICP_ALIGN_SUCCESS;
+}
+
+#define NEED_ALIGNED()                                                                 \
+  if (!h) return SVNICP_ERR_INVALID;                                                   \
+  if (!h->aligned) return fail(h, SVNICP_ERR_INVALID, "no result yet: call svnicp_align first");
+
+int svnicp_get_transformation(svnicp_handle h, double out6[6]) {
+  NEED_ALIGNED();
+  memcpy(out6, h->h_stats, 6 * sizeof(double));
+  return SVNICP_OK;
+}
+int svnicp_get_distribution(svnicp_handle h, double out6[6]) {
+  NEED_ALIGNED();
+  memcpy(out6, h->h_stats + 6, 6 * sizeof(double));
+  return SVNICP_OK;
+}
+int svnicp_get_cov_matrix(svnicp_handle h, double out36[36]) {
+  NEED_ALIGNED();
+  memcpy(out36, h->h_stats + 12, 36 * sizeof(double));
+  return SVNICP_OK;
+}
+int svnicp_get_particles(svnicp_handle h, double *out) {
+  NEED_ALIGNED();
+  memcpy(out, h->h_particles, (size_t)6 * h->P * sizeof(double));
+  return SVNICP_OK;
+}
+int svnicp_get_particle_weight(svnicp_handle h, double *out) {
+  if (!h) return SVNICP_ERR_INVALID;
+  const double w = (double)(1.0f / (float)h->P);  // SVNICP.cpp:46 + :281-284: float32 weights widened to double
+  for (int p = 0; p < h->P; p++) out[p] = w;
+  return SVNICP_OK;
+}
+int svnicp_get_particle_history(svnicp_handle h, float *out, int32_t *rows) {
+  if (!h) return SVNICP_ERR_INVALID;
+  if (!h->aligned) return fail(h, SVNICP_ERR_INVALID, "no result yet");
+  const int I = h->prm.iterations;
+  if (rows) *rows = I;
+  if (out && I > 0) {
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy(out, h->history.p, (size_t)I * 6 * h->P * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return SVNICP_OK;
+}
+int svnicp_get_runtime(svnicp_handle h, double out3[3]) {
+  if (!h) return SVNICP_ERR_INVALID;
+  // SVGDICP.h:94-96 {knn_duration_, update_duration_, finish_iter_}; SVNICP never fills them (Q12) -- we do, from CUDA events.
+  out3[0] = h->ms_setup * 1e-3;
+  out3[1] = h->ms_iter * 1e-3;
+  out3[2] = (double)(h->aligned ? h->iters_done : h->prm.iterations);
+  return SVNICP_OK;
+}
+
+// ---- counter-based RNG for the particle initialisers (ICPUtils.cpp:45-75) ----
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+static inline double u01(uint64_t seed, uint64_t i) { return (double)(splitmix64(seed ^ splitmix64(i)) >> 11) * (1.0 / 9007199254740992.0); }
+
+int svnicp_initialize_particles(int P, const double ub[6], const double lb[6], uint64_t seed, double *out) {
+  if (P < 1 || !ub || !lb || !out) return SVNICP_ERR_INVALID;
+  for (int c = 0; c < 6; c++)
+    for (int p = 0; p < P; p++) out[(size_t)c * P + p] = (P == 1) ? 0.0 : (ub[c] - lb[c]) * u01(seed, (uint64_t)c * P + p) + lb[c];
+  return SVNICP_OK;
+}
+
+int svnicp_initialize_particles_gaussian(int P, const double cov_diag[6], uint64_t seed, double *out) {
+  if (P < 1 || !cov_diag || !out) return SVNICP_ERR_INVALID;
+  for (int c = 0; c < 6; c++) {
+    const double sd = sqrt(cov_diag[c]);
+    for (int p = 0; p < P; p++) {
+      if (P == 1) { out[(size_t)c * P + p] = 0.0; continue; }
+      const double u1 = u01(seed, 2 * ((uint64_t)c * P + p)), u2 = u01(seed, 2 * ((uint64_t)c * P + p) + 1);
+      double z = sqrt(-2.0 * log(u1 > 1e-300 ? u1 : 1e-300)) * cos(6.283185307179586 * u2) * sd;
+      if (z > 3 * sd) z = 3 * sd;   // clamp(-3 sigma, 3 sigma), ICPUtils.cpp:72-74
+      if (z < -3 * sd) z = -3 * sd;
+      out[(size_t)c * P + p] = z;
+    }
+  }
+  return SVNICP_OK;
+}
+
+// ---- parity / debug taps ----
+int svnicp_iterations_done(svnicp_handle h, int32_t *out) {
+  if (!h || !out) return SVNICP_ERR_INVALID;
+  *out = h->iters_done;
+  return SVNICP_OK;
+}
+
+int svnicp_get_candidates(svnicp_handle h, int32_t *out_idx, float *out_rel) {
+  if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
+  CU(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->n_s * h->K;
+  std::vector<float4> tmp(n);
+  CU(cudaMemcpy(tmp.data(), h->cand.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; i++) {
+    if (out_idx) memcpy(&out_idx[i], &tmp[i].w, 4);
+    if (out_rel) { out_rel[3 * i] = tmp[i].x; out_rel[3 * i + 1] = tmp[i].y; out_rel[3 * i + 2] = tmp[i].z; }
+  }
+  return SVNICP_OK;
+}
+
+int svnicp_get_source_f32(svnicp_handle h, float *out) {
+  if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
+  CU(cudaSetDevice(h->device));
+  std::vector<float4> tmp((size_t)h->n_s);
+  CU(cudaMemcpy(tmp.data(), h->sp.p, (size_t)h->n_s * sizeof(float4), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < h->n_s; i++) { out[3 * i] = tmp[i].x; out[3 * i + 1] = tmp[i].y; out[3 * i + 2] = tmp[i].z; }
+  return SVNICP_OK;
+}
+
+int svnicp_get_correspondences(svnicp_handle h, float *out_xf, int32_t *out_idx, uint8_t *out_mask) {
+  if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
+  if (!h->prm.debug_corr) return fail(h, SVNICP_ERR_INVALID, "created without debug_corr");
+  CU(cudaSetDevice(h->device));
+  if (out_xf) CU(cudaMemcpy(out_xf, h->xf.p, (size_t)h->P_l * 12 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out_idx) CU(cudaMemcpy(out_idx, h->dbg_idx.p, (size_t)h->P_l * h->n_s * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (out_mask) CU(cudaMemcpy(out_mask, h->dbg_mask.p, (size_t)h->P_l * h->n_s, cudaMemcpyDeviceToHost));
+  return SVNICP_OK;
+}
+
+int svnicp_get_gn_system(svnicp_handle h, double *out_H, double *out_b, double *out_x) {
+  if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
+  CU(cudaSetDevice(h->device));
+  std::vector<double> rec((size_t)h->P * REC);
+  CU(cudaMemcpy(rec.data(), h->rec.p, rec.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  // x at the head of the last executed iteration lives in xs [6][P] (the epilogue rewrites rec's x with the final poses)
+  std::vector<double> xs((size_t)6 * h->P);
+  CU(cudaMemcpy(xs.data(), h->xs.p, xs.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int p = 0; p < h->P; p++) {
+    const double *r = rec.data() + (size_t)p * REC;
+    if (out_x)
+      for (int c = 0; c < 6; c++) out_x[6 * (size_t)p + c] = xs[(size_t)c * h->P + p];
+    if (out_b) memcpy(out_b + 6 * (size_t)p, r + REC_B, 6 * sizeof(double));
+    if (out_H)
+      for (int a = 0; a < 6; a++)
+        for (int c = 0; c < 6; c++) out_H[36 * (size_t)p + 6 * a + c] = r[REC_H + (a <= c ? tri(a, c) : tri(c, a))];
+  }
+  return SVNICP_OK;
+}
+
+int svnicp_get_stein(svnicp_handle h, double *out_delta, double *out_bandwidth) {
+  if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
+  CU(cudaSetDevice(h->device));
+  if (out_delta) CU(cudaMemcpy(out_delta, h->delta.p, (size_t)h->P_l * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_bandwidth) *out_bandwidth = h->h_ctrl->bandwidth;
+  return SVNICP_OK;
+}
+
+int svnicp_get_prune_stats(svnicp_handle h, double *out_mean_kept, int32_t *rows) {
+  if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
+  const int I = h->prm.iterations;
+  if (rows) *rows = I;
+  if (out_mean_kept)
+    for (int i = 0; i < I; i++) out_mean_kept[i] = (double)h->h_kept[i] / (double)(h->n_s > 0 ? h->n_s : 1);
+  return SVNICP_OK;
+}
+
+int svnicp_get_timing(svnicp_handle h, double out4[4]) {
+  if (!h) return SVNICP_ERR_INVALID;
+  out4[0] = h->ms_setup; out4[1] = h->ms_iter; out4[2] = h->ms_epi; out4[3] = h->ms_total;
+  return SVNICP_OK;
+}
+
+int svnicp_get_slice(svnicp_handle h, int32_t *lo, int32_t *hi) {
+  if (!h) return SVNICP_ERR_INVALID;
+  if (lo) *lo = h->p_lo;
+  if (hi) *hi = h->p_lo + h->P_l;
+  return SVNICP_OK;
+}
+
+int svnicp_set_profiling(svnicp_handle h, int on) {
+  if (!h) return SVNICP_ERR_INVALID;
+  h->profile = on ? 1 : 0;
+  return SVNICP_OK;
+}
+
+int svnicp_get_phase_times(svnicp_handle h, double out8[8]) {
+  if (!h || !out8) return SVNICP_ERR_INVALID;
+  for (int k = 0; k < 8; k++) out8[k] = h->phase_ms[k];
+  return SVNICP_OK;
+}
+
+int svnicp_get_scan_info(svnicp_handle h, int64_t out8[8]) {
+  if (!h || !out8) return SVNICP_ERR_INVALID;
+  out8[0] = h->n_s; out8[1] = h->n_t; out8[2] = h->K; out8[3] = h->fallback_queries;
+  out8[4] = h->TB; out8[5] = h->n_slices; out8[6] = h->n_pgroups; out8[7] = h->enqueued_iters;
+  return SVNICP_OK;
+}
+
+int svnicp_get_launch_count(svnicp_handle h, int64_t *out) {
+  if (!h || !out) return SVNICP_ERR_INVALID;
+  *out = h->launches;
+  return SVNICP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// common.cuh -- shared device-side declarations of the B200 SVN-ICP inner loop.
+//
+// Data layout in HBM (one handle = one GPU = one particle slice):
+//   src64  [N_s][3] f64   clone of the source cloud           (SVGDICP.cpp:56)
+//   tgt64  [N_t][3] f64   clone of the target cloud           (SVGDICP.cpp:55)
+//   sp     [N_s]   float4 (R0*s).xyz, w = |R0*s| rounded up   per scan
+//   cand   [N_s][K] float4 candidate m - q0 (fp32), w = global map index bits; ascending (d0^2, index)
+//   clist  [N_s][K] float4 per-iteration exactly pruned candidate lists, ccount [N_s]
+//   R,t    [P][9],[P][3] f64 particle state (only the local slice is authoritative)
+//   xf     [P_l][12] f32  per-iteration particle transforms A' = R0 (R_p - I) R0^T, tau = R0 t_p
+//   part   [slices*RG][P_l][16] f64 Gauss-Newton partial sums
+//   rec    [P_pad][REC] f64 packed per-particle record (the all-gather payload)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svn {
+
+// packed per-particle record, REC doubles
+constexpr int REC = 40;
+constexpr int REC_X = 0;       // [0,6)   x = [t ; Log R] at the head of the iteration
+constexpr int REC_B = 6;       // [6,12)  b = sum J^T rho e
+constexpr int REC_H = 12;      // [12,33) H upper triangle, row-major
+constexpr int REC_DNORM = 33;  // |delta| of the previous iteration (early stop, SVNICP.cpp:95-101)
+constexpr int REC_G = 34;      // [34,40) g = H^-1 b (pre-conditioned SVGD mode only, SVNICP.cpp:162)
+
+constexpr int NACC = 16;  // W, S1(3), S2(6: xx xy xz yy yz zz), E(3), C(3)
+
+constexpr int MED_PASSES = 5;  // 11 + 13 + 13 + 13 + 13 = 63 key bits
+constexpr int MED_BINS = 8192;
+
+struct Ctrl {
+  int stop;         // 1 once the early stop fired (all later kernels return immediately)
+  int iter;         // iterations whose pose update has been applied
+  int iters_done;   // == iter at the moment of the stop
+  int pad0;
+  double bandwidth;  // h of the last Stein step
+  // exact-pruning ball of the local particle slice (k_prep): |q_pb - qbar_b| <= alpha*|s'_b| + beta
+  float Abar[9];
+  float taubar[3];
+  float alpha;
+  float beta;
+  // median radix select (lower median of P^2 pairwise squared distances, SVNICP.cpp:262)
+  unsigned long long sel_prefix[MED_PASSES + 1];
+  unsigned long long sel_rank[MED_PASSES + 1];
+  unsigned long long kept_total;  // sum of ccount over rows (prune statistics)
+};
+
+struct ScanConst {  // per-scan constants, passed by value
+  double R0[9];
+  double t0[3];
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- 6x6 dense helpers in fp64 (Stein step, finalize) ------------------------------------------
+// LU with partial pivoting; solves A X = B (nrhs columns), row-major, in place on B.
+__device__ inline void lu_solve6(double *A, double *B, int nrhs) {
+  for (int k = 0; k < 6; k++) {
+    int p = k;
+    double mx = fabs(A[k * 6 + k]);
+    for (int i = k + 1; i < 6; i++) {
+      double v = fabs(A[i * 6 + k]);
+      if (v > mx) { mx = v; p = i; }
+    }
+    if (p != k) {
+      for (int j = 0; j < 6; j++) { double t = A[k * 6 + j]; A[k * 6 + j] = A[p * 6 + j]; A[p * 6 + j] = t; }
+      for (int j = 0; j < nrhs; j++) { double t = B[k * nrhs + j]; B[k * nrhs + j] = B[p * nrhs + j]; B[p * nrhs + j] = t; }
+    }
+    const double d = A[k * 6 + k];
+    for (int i = k + 1; i < 6; i++) {
+      const double l = A[i * 6 + k] / d;
+      for (int j = k + 1; j < 6; j++) A[i * 6 + j] -= l * A[k * 6 + j];
+      for (int j = 0; j < nrhs; j++) B[i * nrhs + j] -= l * B[k * nrhs + j];
+    }
+  }
+  for (int k = 5; k >= 0; k--)
+    for (int j = 0; j < nrhs; j++) {
+      double s = B[k * nrhs + j];
+      for (int i = k + 1; i < 6; i++) s -= A[k * 6 + i] * B[i * nrhs + j];
+      B[k * nrhs + j] = s / A[k * 6 + k];
+    }
+}
+
+// upper-triangle index of (r,c), r <= c, row-major packing of a symmetric 6x6
+__host__ __device__ __forceinline__ int tri(int r, int c) { return r * 6 - (r * (r - 1)) / 2 + (c - r); }
+
+// SO(3) Exp and left Jacobian exactly as SVNICP::to_rotation_tensor (SVNICP.cpp:166-194),
+// NaN at angle == 0 for J_l included (quirk Q7).
+__device__ inline void so3_exp(const double r[3], double R[9], double *Jl) {
+  const double a = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  double n[3];
+  if (a < 1e-12) { n[0] = n[1] = n[2] = 0.0; }
+  else { n[0] = r[0] / a; n[1] = r[1] / a; n[2] = r[2] / a; }
+  const double c = cos(a), s = sin(a);
+  const double ah[9] = {0, -n[2], n[1], n[2], 0, -n[0], -n[1], n[0], 0};
+  const double sa = s / a, ca = (1.0 - c) / a;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      const double id = (i == j) ? 1.0 : 0.0, nn = n[i] * n[j];
+      R[3 * i + j] = c * id + (1.0 - c) * nn + s * ah[3 * i + j];
+      if (Jl) Jl[3 * i + j] = sa * id + (1.0 - sa) * nn + ca * ah[3 * i + j];
+    }
+}
+
+// SO(3) Log exactly as SVNICP::rotm_to_ypr_tensor (SVNICP.cpp:196-215).
+__device__ inline void so3_log(const double R[9], double w[3]) {
+  double v = 0.5 * (R[0] + R[4] + R[8] - 1.0);
+  v = fmin(fmax(v, -1.0), 1.0);
+  const double a = acos(v), s = sin(a);
+  if (fabs(s) > 1e-12) {
+    const double f = 0.5 / s * a;
+    w[0] = f * (R[7] - R[5]);
+    w[1] = f * (R[2] - R[6]);
+    w[2] = f * (R[3] - R[1]);
+  } else {
+    w[0] = w[1] = w[2] = 0.0;
+  }
+}
+
+}  // namespace svn

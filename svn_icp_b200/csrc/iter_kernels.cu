@@ -1,0 +1,490 @@
+// iter_kernels.cu -- the per-iteration correspondence + Gauss-Newton pass (north_star kernels (a)+(b)).
+//
+// Replaces, per iteration of SVNICP::stein_align (reference svn-icp/src/core/SVNICP.cpp:52-71):
+//   transform            SVNICP.cpp:58-64
+//   get_correspondence_fast + KNearestNeighborKernelV3<double,3,1>   SVGDICP.cpp:300-329, knn.cu:204-251
+//   point_filter         SVGDICP.cpp:331-333
+//   Newton_grad_right    SVNICP.cpp:116-164  (J [P,B,3,6] is never materialised)
+//
+//   k_prep     fp64 particle state -> fp32 transforms in coordinates RELATIVE to q0_b, plus the ball
+//              (centre transform, alpha, beta) that bounds every particle's query around the centre query.
+//   k_filter   HBM-streaming pass over the candidate table: per source point keeps exactly the candidates
+//              that can be the nearest neighbour of ANY particle of the slice (triangle inequality around
+//              the centre query), in slot order.  Reads 16*N_s*(K+1) bytes: the HBM-roofline kernel.
+//   k_gn       fused transform + 1-NN over the pruned lists + robust weight + Gauss-Newton reduction.
+//              Lists are staged through shared memory with 1-D TMA bulk copies (cp.async.bulk +
+//              mbarrier, a dedicated producer warp, S stages); one thread owns one particle and keeps
+//              its 16 sums in registers (fp32 per tile, folded into fp64), so no cross-thread reduction
+//              is needed until the per-CTA partials are summed by k_finalize.
+//   k_finalize fixed-order fp64 sum of the partials -> H (21), b (6) of the reference's system.
+//
+// Arithmetic that decides a correspondence index is written with explicit _rn intrinsics and is restated
+// operation by operation in oracle/svn_oracle.c (oracle_corr_f32) for the bit-exact index parity test.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace svn {
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk TMA
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// k_prep
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_prep(IterArgs a) {
+  if (a.ctrl->stop) return;
+  __shared__ double s_red[32][12];
+  __shared__ float s_center[12];
+  __shared__ double s_max[32][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double *R0 = a.sc.R0;
+  double acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) acc[i] = 0.0;
+  for (int l = tid; l < a.P_l; l += blockDim.x) {
+    const int p = a.p_lo + l;
+    double R[9], t[3], w[3];
+#pragma unroll
+    for (int i = 0; i < 9; i++) R[i] = a.R[9 * (size_t)p + i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) t[i] = a.t[3 * (size_t)p + i];
+    so3_log(R, w);  // SVNICP.cpp:74-77
+    double *rec = a.rec + (size_t)p * REC;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { rec[REC_X + i] = t[i]; rec[REC_X + 3 + i] = w[i]; }
+    rec[REC_DNORM] = a.dnorm[l];
+    // A' = R0 (R - I) R0^T, tau = R0 t   (so that q_pb - q0_b = A' (R0 s_b) + tau)
+    double D[9], T[9], M[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) D[i] = R[i] - ((i % 4 == 0) ? 1.0 : 0.0);
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) T[3 * r + c] = R0[3 * r] * D[c] + R0[3 * r + 1] * D[3 + c] + R0[3 * r + 2] * D[6 + c];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) M[3 * r + c] = T[3 * r] * R0[3 * c] + T[3 * r + 1] * R0[3 * c + 1] + T[3 * r + 2] * R0[3 * c + 2];
+    float *xf = a.xf + (size_t)l * 12;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { const float f = __double2float_rn(M[i]); xf[i] = f; acc[i] += (double)f; }
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const float f = __double2float_rn(R0[3 * r] * t[0] + R0[3 * r + 1] * t[1] + R0[3 * r + 2] * t[2]);
+      xf[9 + r] = f;
+      acc[9 + r] += (double)f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) acc[i] = warp_sum(acc[i]);
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 12; i++) s_red[warp][i] = acc[i];
+  __syncthreads();
+  if (tid < 12) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += s_red[w][tid];
+    s_center[tid] = __double2float_rn(s / (double)a.P_l);
+  }
+  __syncthreads();
+  double ma = 0.0, mb = 0.0;
+  for (int l = tid; l < a.P_l; l += blockDim.x) {
+    const float *xf = a.xf + (size_t)l * 12;
+    double da = 0, db = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { const double d = (double)xf[i] - (double)s_center[i]; da += d * d; }
+#pragma unroll
+    for (int i = 9; i < 12; i++) { const double d = (double)xf[i] - (double)s_center[i]; db += d * d; }
+    // NaN state (e.g. the reference's P == 2 bandwidth-0 quirk) must poison the radius, not vanish in fmax
+    ma = (da != da) ? da : fmax(ma, da);
+    mb = (db != db) ? db : fmax(mb, db);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oa = __shfl_xor_sync(0xffffffffu, ma, o), ob = __shfl_xor_sync(0xffffffffu, mb, o);
+    ma = (oa != oa || ma != ma) ? NAN : fmax(ma, oa);
+    mb = (ob != ob || mb != mb) ? NAN : fmax(mb, ob);
+  }
+  if (lane == 0) { s_max[warp][0] = ma; s_max[warp][1] = mb; }
+  __syncthreads();
+  if (tid == 0) {
+    double fa = 0, fb = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+      fa = (s_max[w][0] != s_max[w][0] || fa != fa) ? NAN : fmax(fa, s_max[w][0]);
+      fb = (s_max[w][1] != s_max[w][1] || fb != fb) ? NAN : fmax(fb, s_max[w][1]);
+    }
+    Ctrl *c = a.ctrl;
+    for (int i = 0; i < 9; i++) c->Abar[i] = s_center[i];
+    for (int i = 0; i < 3; i++) c->taubar[i] = s_center[9 + i];
+    c->alpha = __double2float_ru(sqrt(fa) * (1.0 + 1e-6));
+    c->beta = __double2float_ru(sqrt(fb) * (1.0 + 1e-6));
+    c->kept_total = 0ull;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_filter: exact candidate pruning, one warp per source point
+// ---------------------------------------------------------------------------------------------
+constexpr float PRUNE_MARGIN = 1e-4f;  // metres; absorbs every fp32 rounding in q, qbar and the norms
+
+template <int NCH>
+__global__ void __launch_bounds__(256) k_filter(IterArgs a) {
+  if (a.ctrl->stop) return;
+  const int lane = lane_id();
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const Ctrl *c = a.ctrl;
+  float A[9], tb[3];
+#pragma unroll
+  for (int i = 0; i < 9; i++) A[i] = c->Abar[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) tb[i] = c->taubar[i];
+  const float alpha = c->alpha, beta = c->beta;
+  const int K = a.K;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned long long kept = 0;
+  for (int b = gw; b < a.n_s; b += nw) {
+    const float4 s = a.sp[b];
+    const float qx = fmaf(A[0], s.x, fmaf(A[1], s.y, fmaf(A[2], s.z, tb[0])));
+    const float qy = fmaf(A[3], s.x, fmaf(A[4], s.y, fmaf(A[5], s.z, tb[1])));
+    const float qz = fmaf(A[6], s.x, fmaf(A[7], s.y, fmaf(A[8], s.z, tb[2])));
+    const float rho = fmaf(alpha, s.w, beta);
+    const float4 *row = a.cand + (size_t)b * K;
+    float4 e[NCH];
+    float d2[NCH];
+    float dmin = INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+      const int k = ch * 32 + lane;
+      if (k < K) {
+        e[ch] = row[k];
+        const float dx = qx - e[ch].x, dy = qy - e[ch].y, dz = qz - e[ch].z;
+        d2[ch] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        dmin = fminf(dmin, d2[ch]);  // fminf drops NaN: a NaN d2 never becomes the minimum
+      } else {
+        d2[ch] = INFINITY;
+      }
+    }
+    dmin = warp_min(dmin);
+    // any candidate farther than d_min + 2 rho from the centre query cannot be (or tie with) the
+    // nearest neighbour of a query within rho of it
+    const float lim = sqrtf(dmin) + 2.0f * rho + PRUNE_MARGIN;
+    const float thr = lim * lim * (1.0f + 1e-5f);
+    float4 *out = a.clist + (size_t)b * K;
+    int base = 0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+      const int k = ch * 32 + lane;
+      const bool keep = (k < K) && !(d2[ch] > thr);  // NaN anywhere keeps everything (NaN must propagate)
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) out[base + __popc(m & lt)] = e[ch];
+      base += __popc(m);
+    }
+    if (lane == 0) { a.ccount[b] = base; kept += (unsigned long long)base; }
+  }
+  if (lane == 0 && kept) atomicAdd(&a.ctrl->kept_total, kept);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_gn: fused transform + 1-NN + robust weight + Gauss-Newton reduction
+// ---------------------------------------------------------------------------------------------
+constexpr int GN_CONSUMERS = 256;
+constexpr int GN_THREADS = GN_CONSUMERS + 32;
+constexpr int GN_FLUSH_ROWS = 16;
+
+template <bool DBG>
+__global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {
+  if (a.ctrl->stop) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int TB = a.TB, K = a.K, S = a.stages;
+  const size_t stage_bytes = gn_stage_bytes(TB, K);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_bytes);
+  uint64_t *empty = full + S;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = a.n_pad / TB;
+  const int slice = blockIdx.x, n_slices = gridDim.x;
+  const int n_my = (slice < n_tiles) ? (n_tiles - slice + n_slices - 1) / n_slices : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(full + s, 1); mbar_init(empty + s, GN_CONSUMERS / 32); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == GN_CONSUMERS / 32) {
+    // ---------------- producer warp: 1-D TMA bulk copies of the pruned lists ----------------
+    for (int i = 0; i < n_my; i++) {
+      const int s = i % S, k = i / S;
+      mbar_wait(empty + s, (uint32_t)((k & 1) ^ 1));
+      const int row0 = (slice + i * n_slices) * TB;
+      unsigned char *st = smem + (size_t)s * stage_bytes;
+      const int cnt = (lane < TB) ? a.ccount[row0 + lane] : 0;
+      int bytes = cnt * 16;
+      int total = bytes;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      total += TB * 16 + TB * 4;
+      if (lane == 0) mbar_expect_tx(full + s, (uint32_t)total);
+      __syncwarp();
+      if (lane < TB && cnt > 0) bulk_g2s(st + (size_t)lane * K * 16, a.clist + (size_t)(row0 + lane) * K, (uint32_t)bytes, full + s);
+      if (lane == 0) {
+        bulk_g2s(st + (size_t)TB * K * 16, a.sp + row0, (uint32_t)(TB * 16), full + s);
+        bulk_g2s(st + (size_t)TB * K * 16 + (size_t)TB * 16, a.ccount + row0, (uint32_t)(TB * 4), full + s);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers: one thread = one particle (x RG row groups) ----------------
+  const int PG = a.PG, RG = a.RG;
+  const int pl = tid % PG, rg = tid / PG;
+  const int l = blockIdx.y * PG + pl;  // local particle index
+  const bool active = l < a.P_l;
+  float A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, A6 = 0, A7 = 0, A8 = 0, t0 = 0, t1 = 0, t2 = 0;
+  if (active) {
+    const float *xf = a.xf + (size_t)l * 12;
+    A0 = xf[0]; A1 = xf[1]; A2 = xf[2]; A3 = xf[3]; A4 = xf[4]; A5 = xf[5]; A6 = xf[6]; A7 = xf[7]; A8 = xf[8];
+    t0 = xf[9]; t1 = xf[10]; t2 = xf[11];
+  }
+  const float Dm = a.max_dist;
+  float acc[NACC];
+  double dacc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) { acc[i] = 0.f; dacc[i] = 0.0; }
+  int rows_in_acc = 0;
+
+  for (int i = 0; i < n_my; i++) {
+    const int s = i % S, k = i / S;
+    mbar_wait(full + s, (uint32_t)(k & 1));
+    const unsigned char *st = smem + (size_t)s * stage_bytes;
+    const float4 *ent = reinterpret_cast<const float4 *>(st);
+    const float4 *src = reinterpret_cast<const float4 *>(st + (size_t)TB * K * 16);
+    const int *cnt = reinterpret_cast<const int *>(st + (size_t)TB * K * 16 + (size_t)TB * 16);
+    if (active) {
+      for (int r = rg; r < TB; r += RG) {
+        const int n = cnt[r];
+        if (n == 0) continue;  // padding row
+        const float4 sv = src[r];
+        // a = A' s' ; q = a + tau : query relative to q0_b.  Order fixed (index parity).
+        const float ax = __fmaf_rn(A0, sv.x, __fmaf_rn(A1, sv.y, __fmul_rn(A2, sv.z)));
+        const float ay = __fmaf_rn(A3, sv.x, __fmaf_rn(A4, sv.y, __fmul_rn(A5, sv.z)));
+        const float az = __fmaf_rn(A6, sv.x, __fmaf_rn(A7, sv.y, __fmul_rn(A8, sv.z)));
+        const float qx = __fadd_rn(ax, t0), qy = __fadd_rn(ay, t1), qz = __fadd_rn(az, t2);
+        const float4 *e = ent + (size_t)r * K;
+        float best = INFINITY;
+        int bi = 0;
+        int kk = 0;
+        for (; kk + 4 <= n; kk += 4) {
+          float4 c[4];
+          float d[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) c[u] = e[kk + u];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const float dx = __fsub_rn(qx, c[u].x), dy = __fsub_rn(qy, c[u].y), dz = __fsub_rn(qz, c[u].z);
+            d[u] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (d[u] < best) { best = d[u]; bi = kk + u; }  // strict '<', first slot wins (mink.cuh:141)
+        }
+        for (; kk < n; kk++) {
+          const float4 c = e[kk];
+          const float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
+          const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+          if (d < best) { best = d; bi = kk; }
+        }
+        const float4 cw = e[bi];
+        const float ex = __fsub_rn(qx, cw.x), ey = __fsub_rn(qy, cw.y), ez = __fsub_rn(qz, cw.z);
+        const bool valid = best < Dm;  // SVGDICP.cpp:332: squared distance vs un-squared max_dist (Q1)
+        if (DBG) {
+          const int row = (slice + i * n_slices) * TB + r;
+          a.dbg_idx[(size_t)l * a.n_s + row] = __float_as_int(cw.w);
+          a.dbg_mask[(size_t)l * a.n_s + row] = valid ? 1 : 0;
+        }
+        // rho = (D / (D + 3 |e|))^2  (SVNICP.cpp:120-122); masked pairs: rho' = 0 and +1 on the translation block (Q2)
+        const float en = sqrtf(best);
+        const float wq = __fdividef(Dm, fmaf(3.0f, en, Dm));
+        const float rho = wq * wq;
+        const float rp = valid ? rho : 0.0f;
+        acc[0] += valid ? rho : 1.0f;
+        const float gx = rp * sv.x, gy = rp * sv.y, gz = rp * sv.z;
+        acc[1] += gx; acc[2] += gy; acc[3] += gz;
+        acc[4] = fmaf(gx, sv.x, acc[4]); acc[5] = fmaf(gx, sv.y, acc[5]); acc[6] = fmaf(gx, sv.z, acc[6]);
+        acc[7] = fmaf(gy, sv.y, acc[7]); acc[8] = fmaf(gy, sv.z, acc[8]); acc[9] = fmaf(gz, sv.z, acc[9]);
+        const float fx = rp * ex, fy = rp * ey, fz = rp * ez;  // multiplication (not select): NaN must propagate
+        acc[10] += fx; acc[11] += fy; acc[12] += fz;
+        const float wx = ax + sv.x, wy = ay + sv.y, wz = az + sv.z;  // R~ s in the world-oriented frame
+        acc[13] = fmaf(wy, fz, fmaf(-wz, fy, acc[13]));
+        acc[14] = fmaf(wz, fx, fmaf(-wx, fz, acc[14]));
+        acc[15] = fmaf(wx, fy, fmaf(-wy, fx, acc[15]));
+        rows_in_acc++;
+      }
+      if (rows_in_acc >= GN_FLUSH_ROWS) {
+#pragma unroll
+        for (int j = 0; j < NACC; j++) { dacc[j] += (double)acc[j]; acc[j] = 0.f; }
+        rows_in_acc = 0;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+  if (active) {
+    double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + l) * NACC;
+#pragma unroll
+    for (int j = 0; j < NACC; j++) out[j] = dacc[j] + (double)acc[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_finalize: partials -> reference H (upper triangle) and b; one warp per particle
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_finalize(IterArgs a) {
+  if (a.ctrl->stop) return;
+  const int lane = lane_id();
+  const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (l >= a.P_l) return;
+  const int nrows = a.n_slices * a.RG;
+  double s = 0.0;
+  if (lane < NACC)
+    for (int r = 0; r < nrows; r++) s += a.part[((size_t)r * a.P_l + l) * NACC + lane];  // fixed order
+  double v[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; j++) v[j] = __shfl_sync(0xffffffffu, s, j);
+  if (lane != 0) return;
+  const int p = a.p_lo + l;
+  const double *R0 = a.sc.R0;
+  double Rp[9], Rt[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rp[i] = a.R[9 * (size_t)p + i];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) Rt[3 * r + c] = R0[3 * r] * Rp[c] + R0[3 * r + 1] * Rp[3 + c] + R0[3 * r + 2] * Rp[6 + c];
+  const double W = v[0];
+  // world-oriented -> sensor frame: S1 = R0^T S1', S2 = R0^T S2' R0
+  const double S1p[3] = {v[1], v[2], v[3]};
+  const double S2p[9] = {v[4], v[5], v[6], v[5], v[7], v[8], v[6], v[8], v[9]};
+  double S1[3], T[9], S2[9];
+#pragma unroll
+  for (int c = 0; c < 3; c++) S1[c] = R0[c] * S1p[0] + R0[3 + c] * S1p[1] + R0[6 + c] * S1p[2];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) T[3 * r + c] = R0[r] * S2p[c] + R0[3 + r] * S2p[3 + c] + R0[6 + r] * S2p[6 + c];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) S2[3 * r + c] = T[3 * r] * R0[c] + T[3 * r + 1] * R0[3 + c] + T[3 * r + 2] * R0[6 + c];
+  double H[36];
+#pragma unroll
+  for (int i = 0; i < 36; i++) H[i] = 0.0;
+  const double trS2 = S2[0] + S2[4] + S2[8];
+  for (int i = 0; i < 3; i++) {
+    H[7 * i] = W + 1e-6;  // SVNICP.cpp:153 (Q3); translation block = sum(rho') + #masked (Q2)
+    for (int j = 0; j < 3; j++) H[6 * (3 + i) + 3 + j] = ((i == j) ? trS2 : 0.0) - S2[3 * i + j];
+    H[7 * (3 + i)] += 1e-6;
+  }
+  // H_tr = -[S1]x
+  H[0 * 6 + 4] = S1[2];  H[0 * 6 + 5] = -S1[1];
+  H[1 * 6 + 3] = -S1[2]; H[1 * 6 + 5] = S1[0];
+  H[2 * 6 + 3] = S1[1];  H[2 * 6 + 4] = -S1[0];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) H[6 * (3 + i) + j] = H[6 * j + 3 + i];
+  double b[6];
+  // b_t = R~^T E, b_r = R~^T C
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    b[c] = Rt[c] * v[10] + Rt[3 + c] * v[11] + Rt[6 + c] * v[12];
+    b[3 + c] = Rt[c] * v[13] + Rt[3 + c] * v[14] + Rt[6 + c] * v[15];
+  }
+  double *rec = a.rec + (size_t)p * REC;
+#pragma unroll
+  for (int i = 0; i < 6; i++) rec[REC_B + i] = b[i];
+  for (int r = 0; r < 6; r++)
+    for (int c = r; c < 6; c++) rec[REC_H + tri(r, c)] = H[6 * r + c];
+  if (!a.svn_full_grad) {  // g = H^-1 b, SVNICP.cpp:162 (only consumed by the pre-conditioned SVGD step)
+    double g[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) g[i] = b[i];
+    lu_solve6(H, g, 1);
+#pragma unroll
+    for (int i = 0; i < 6; i++) rec[REC_G + i] = g[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+void init_iter_kernels() {
+  cudaFuncSetAttribute(k_gn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_gn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+int launch_prep(const IterArgs &a, cudaStream_t st) {
+  k_prep<<<1, 1024, 0, st>>>(a);
+  return 1;
+}
+
+int launch_filter(const IterArgs &a, cudaStream_t st) {
+  const int nch = (a.K + 31) / 32;
+  int grid = cdiv((long long)a.n_s * 32, 256);
+  const int max_grid = a.sm_count * 8;
+  if (grid > max_grid) grid = max_grid;
+  if (grid < 1) grid = 1;
+  switch (nch) {
+    case 1: k_filter<1><<<grid, 256, 0, st>>>(a); break;
+    case 2: k_filter<2><<<grid, 256, 0, st>>>(a); break;
+    case 3: k_filter<3><<<grid, 256, 0, st>>>(a); break;
+    case 4: k_filter<4><<<grid, 256, 0, st>>>(a); break;
+    case 5: k_filter<5><<<grid, 256, 0, st>>>(a); break;
+    case 6: k_filter<6><<<grid, 256, 0, st>>>(a); break;
+    case 7: k_filter<7><<<grid, 256, 0, st>>>(a); break;
+    default: k_filter<8><<<grid, 256, 0, st>>>(a); break;
+  }
+  return 1;
+}
+
+int launch_gn(const IterArgs &a, cudaStream_t st) {
+  dim3 grid(a.n_slices, a.n_pgroups);
+  if (a.dbg_idx) k_gn<true><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
+  else k_gn<false><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
+  return 1;
+}
+
+int launch_finalize(const IterArgs &a, cudaStream_t st) {
+  k_finalize<<<cdiv((long long)a.P_l * 32, 128), 128, 0, st>>>(a);
+  return 1;
+}
+
+}  // namespace svn

@@ -1,0 +1,90 @@
+// kernels.h -- host-callable launchers of the hand-written sm_100a kernels (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace svn {
+
+struct CandBuildArgs {
+  const double *src64, *tgt64;
+  int n_s, n_pad, n_t, K;
+  ScanConst sc;
+  double cell;
+  double *q0;     // [n_s][3]
+  float4 *sp;     // [n_pad]
+  // voxel hash of the map
+  unsigned long long *keys;
+  int *counts, *starts, *fill, *pt_slot, *cursor;
+  int table_size;  // power of two >= 2*n_t
+  double *sxyz;    // [n_t][3] cell-sorted map
+  int *sidx;       // [n_t] original indices
+  float4 *cand;    // [n_s][K]
+  int *fallback_count;
+  int sm_count;
+};
+int launch_cand_build(const CandBuildArgs &a, cudaStream_t st);
+size_t knn_smem_bytes();
+
+struct IterArgs {
+  // sizes
+  int n_s, n_pad, K;
+  int P;            // all particles
+  int p_lo, P_l;    // local slice
+  // geometry
+  ScanConst sc;
+  float max_dist;
+  // buffers
+  const float4 *sp, *cand;
+  float4 *clist;
+  int *ccount;
+  double *R, *t;       // [P][9], [P][3]
+  float *xf;           // [P_l][12]
+  double *dnorm;       // [P_l]
+  double *part;        // [n_slices*RG][P_l][NACC]
+  double *rec;         // [P_pad][REC]
+  Ctrl *ctrl;
+  // launch shape of the Gauss-Newton kernel
+  int TB, stages, n_slices, n_pgroups, PG, RG;
+  size_t gn_smem;
+  int sm_count;
+  int svn_full_grad;
+  // debug taps (may be null)
+  int32_t *dbg_idx;
+  uint8_t *dbg_mask;
+};
+int launch_prep(const IterArgs &a, cudaStream_t st);
+int launch_filter(const IterArgs &a, cudaStream_t st);
+int launch_gn(const IterArgs &a, cudaStream_t st);
+int launch_finalize(const IterArgs &a, cudaStream_t st);
+void init_iter_kernels();
+// bytes of one shared-memory stage of k_gn: TB pruned rows of K float4 + TB source points + TB counts
+__host__ __device__ inline size_t gn_stage_bytes(int TB, int K) { return (size_t)TB * K * 16 + (size_t)TB * 16 + (size_t)TB * 4; }
+
+struct SteinArgs {
+  int P, p_lo, P_l, I;
+  int svn_full_grad, check_early_stop;
+  double lr, threshold;
+  double *rec;       // [P_pad][REC]
+  double *xs;        // [6][P] SoA copy of x
+  double *delta;     // [P_l][6]
+  double *dnorm;     // [P_l]
+  double *R, *t;
+  double *Hbar_inv;  // [36]
+  unsigned *hist;    // [MED_PASSES][MED_BINS]
+  float *history;    // [I][6][P]
+  Ctrl *ctrl;
+  double *stats;     // [6 + 6 + 36] mean, var, cov
+  double *particles; // [6][P]
+  unsigned long long *kept_hist;  // [I] candidates kept by the prune pass per iteration (statistics)
+  int sm_count;
+};
+int launch_decide(const SteinArgs &a, cudaStream_t st, int epilogue);
+int launch_median(const SteinArgs &a, cudaStream_t st);
+int launch_stein(const SteinArgs &a, cudaStream_t st);
+int launch_update(const SteinArgs &a, cudaStream_t st);
+int launch_stats(const SteinArgs &a, cudaStream_t st);
+int launch_init_particles(double *R, double *t, const double *init_pose_dev, int P, double *dnorm, int p_lo, int P_l, Ctrl *ctrl,
+                          cudaStream_t st);
+
+}  // namespace svn

@@ -1,0 +1,235 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed golden vectors.
+
+Bars (BASELINE.json north_star):
+  * correspondence indices bit-exact given identical transformed points and the documented tie-break;
+  * per-particle poses, particle mean and covariance within POSE_TOL = 1e-5 (m / rad) of the fp64 reference.
+"""
+import numpy as np
+import pytest
+
+import oracle as orc
+import svn_icp_b200 as sv
+from svn_icp_b200 import synth
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-5  # metres / radians, stated tolerance for poses, mean and (sqrt of) covariance entries
+
+
+def make_icp(pb, **kw):
+    prm = sv.SteinICPParam(**kw)
+    icp = sv.SVNICP(prm, pb.init_pose, sv.ParticleWeightOpt())
+    icp.add_cloud(pb.source, pb.target, pb.init_pose)
+    icp.set_initial_mean(pb.R0, pb.t0)
+    return icp
+
+
+def initial_state(oracle, init_pose):
+    P = init_pose.shape[1]
+    R = np.stack([oracle.so3_exp(init_pose[3:, p])[0] for p in range(P)])
+    t = np.ascontiguousarray(init_pose[:3].T)
+    return R, t
+
+
+@pytest.fixture(scope="module")
+def small():
+    return synth.make_uniform_problem(40, 1500, 20000, seed=5)
+
+
+@pytest.fixture(scope="module")
+def lidar():
+    # 32-beam x 900 column synthetic scan against a 6-scan voxel map: realistic density, oracle-sized
+    return synth.make_problem(64, sensor="32", scan_index=6, n_map_scans=6, seed=0xC0FFEE)
+
+
+@pytest.mark.parametrize("which,K", [("small", 20), ("small", 100), ("lidar", 100), ("lidar", 33)])
+def test_candidate_table_exact(oracle, request, which, K):
+    """Per-scan K-NN: same K-nearest SET as the reference's brute force (MinK), emitted ascending (d0^2, index)."""
+    pb = request.getfixturevalue(which)
+    icp = make_icp(pb, iterations=0, KNN_count=K, max_dist=3.0)
+    assert icp.stein_align() == sv.ALIGN_SUCCESS
+    idx, rel = icp.get_candidates(want_rel=True)
+    q0 = oracle.transform_q0(pb.source, pb.R0, pb.t0)
+    oidx, orel = oracle.cand_sorted(q0, pb.target, K)
+    np.testing.assert_array_equal(idx, oidx)
+    np.testing.assert_array_equal(rel, orel)
+    np.testing.assert_array_equal(icp.get_source_f32(), oracle.source_f32(pb.source, pb.R0))
+    # same set as the reference's MinK table (slot order differs by design)
+    mink, _ = oracle.knn_mink(q0[:300], pb.target, K)
+    np.testing.assert_array_equal(np.sort(mink, axis=1), np.sort(idx[:300].astype(np.int64), axis=1))
+
+
+def test_candidate_table_tiny_map(oracle):
+    """N_t < K: the reference zero-pads (knn.cu:343) -> padded slots point at map point 0."""
+    pb = synth.make_uniform_problem(5, 60, 60, seed=16, box=8.0)
+    pb.target = pb.target[:10].copy()
+    icp = make_icp(pb, iterations=0, KNN_count=16)
+    icp.stein_align()
+    idx = icp.get_candidates()
+    q0 = oracle.transform_q0(pb.source, pb.R0, pb.t0)
+    oidx, _ = oracle.cand_sorted(q0, pb.target, 16)
+    np.testing.assert_array_equal(idx, oidx)
+    assert np.all(idx[:, 10:] == 0)
+
+
+@pytest.mark.parametrize("which", ["small", "lidar"])
+def test_correspondence_indices_bit_exact(oracle, request, which):
+    """Indices chosen by the fused kernel == oracle restatement of the same fp32 arithmetic on the same inputs; the
+    exact pruning pass must not change a single index."""
+    pb = request.getfixturevalue(which)
+    icp = make_icp(pb, iterations=1, KNN_count=100, max_dist=3.0, debug_corr=True)
+    icp.stein_align()
+    xf, idx, mask = icp.get_correspondences()
+    cidx, rel = icp.get_candidates(want_rel=True)
+    sp = icp.get_source_f32()
+    oidx, omask = oracle.corr_f32(xf, sp, rel, cidx, 3.0)
+    np.testing.assert_array_equal(idx, oidx)
+    np.testing.assert_array_equal(mask, omask)
+    # transforms from the fp64 state
+    R, t = initial_state(oracle, pb.init_pose)
+    np.testing.assert_allclose(xf, oracle.transforms_f32(R, t, pb.R0), rtol=0, atol=2e-7)
+    # against the reference semantics in fp64 (different arithmetic): only near-ties may differ
+    q0 = oracle.transform_q0(pb.source, pb.R0, pb.t0)
+    mink, _ = oracle.knn_mink(q0, pb.target, 100)
+    _, _, ridx, rmask = oracle.gn(R, t, pb.R0, pb.t0, pb.source, pb.target, mink, 3.0, want_corr=True)
+    assert np.mean(ridx != idx) < 1e-4
+    assert np.mean(rmask != mask) < 1e-4
+
+
+@pytest.mark.parametrize("which,P", [("small", 40), ("lidar", 64), ("lidar", 7), ("lidar", 300)])
+def test_gauss_newton_system(oracle, request, which, P):
+    """H (6x6) and b (6) per particle against the fp64 oracle (Newton_grad_right, SVNICP.cpp:116-164)."""
+    pb = request.getfixturevalue(which)
+    rng = np.random.default_rng(P)
+    init = synth.init_particles(P, rng)
+    icp = sv.SVNICP(sv.SteinICPParam(iterations=1, KNN_count=100, max_dist=3.0), init)
+    icp.add_cloud(pb.source, pb.target, init)
+    icp.set_initial_mean(pb.R0, pb.t0)
+    icp.stein_align()
+    H, b, x = icp.get_gn_system()
+    R, t = initial_state(oracle, init)
+    q0 = oracle.transform_q0(pb.source, pb.R0, pb.t0)
+    mink, _ = oracle.knn_mink(q0, pb.target, 100)
+    oH, ob = oracle.gn(R, t, pb.R0, pb.t0, pb.source, pb.target, mink, 3.0)
+    # fp32 geometry + a handful of near-tie correspondences: relative to the block scale
+    for blk in (slice(0, 3), slice(3, 6)):
+        for blk2 in (slice(0, 3), slice(3, 6)):
+            scale = np.abs(oH[:, blk, blk2]).max()
+            np.testing.assert_allclose(H[:, blk, blk2], oH[:, blk, blk2], rtol=0, atol=2e-6 * scale)
+    np.testing.assert_allclose(b[:, :3], ob[:, :3], rtol=0, atol=2e-6 * np.abs(ob[:, :3]).max() + 1e-3)
+    np.testing.assert_allclose(b[:, 3:], ob[:, 3:], rtol=0, atol=2e-6 * np.abs(ob[:, 3:]).max() + 1e-2)
+    np.testing.assert_allclose(x[:, :3], t, rtol=0, atol=1e-15)
+    # the Newton step itself
+    g = np.linalg.solve(H, b[..., None])[..., 0]
+    og = np.linalg.solve(oH, ob[..., None])[..., 0]
+    np.testing.assert_allclose(g, og, rtol=0, atol=POSE_TOL)
+
+
+@pytest.mark.parametrize("full", [True, False])
+@pytest.mark.parametrize("P", [3, 64, 513])
+def test_stein_step(oracle, lidar, full, P):
+    """Kernel (c): bandwidth (exact lower median of P^2 distances) and the update delta, fp64 vs oracle on the GPU's own H,b,x."""
+    rng = np.random.default_rng(100 + P)
+    init = synth.init_particles(P, rng)
+    icp = sv.SVNICP(sv.SteinICPParam(iterations=1, KNN_count=50, max_dist=3.0, SVN_full_grad=full, lr=0.7), init)
+    icp.add_cloud(lidar.source[::4], lidar.target, init)
+    icp.set_initial_mean(lidar.R0, lidar.t0)
+    icp.stein_align()
+    H, b, x = icp.get_gn_system()
+    delta, h = icp.get_stein()
+    od, oh = oracle.stein_step(x, H, b, full=full, lr=0.7)
+    assert h == pytest.approx(oh, rel=1e-13)
+    np.testing.assert_allclose(delta, od, rtol=1e-8, atol=1e-12)
+    # pose update (SVNICP.cpp:268-279) applied to the initial state
+    R, t = initial_state(oracle, init)
+    R2, t2 = oracle.pose_update(R, t, od)
+    want = np.concatenate([t2, np.stack([oracle.so3_log(r) for r in R2])], axis=1)  # [P,6]
+    got = icp.get_particles().reshape(6, P).T
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("full", [True, False])
+def test_full_scan_vs_oracle(oracle, lidar, full):
+    """Whole scan, 12 iterations: poses, mean, variance, covariance, history within the stated tolerance."""
+    icp = make_icp(lidar, iterations=12, KNN_count=100, max_dist=3.0, lr=1.0, SVN_full_grad=full)
+    assert icp.stein_align() == sv.ALIGN_SUCCESS
+    prm = orc.make_params(iterations=12, knn_count=100, max_dist=3.0, lr=1.0, svn_full_grad=full)
+    o = oracle.align(prm, lidar.source, lidar.target, lidar.init_pose, lidar.R0, lidar.t0)
+    P = lidar.init_pose.shape[1]
+    np.testing.assert_allclose(icp.get_particles().reshape(6, P), o["particles"], rtol=0, atol=POSE_TOL)
+    np.testing.assert_allclose(icp.get_transformation(), o["mean"], rtol=0, atol=POSE_TOL)
+    np.testing.assert_allclose(np.sqrt(icp.get_distribution()), np.sqrt(o["var"]), rtol=0, atol=POSE_TOL)
+    np.testing.assert_allclose(icp.get_cov_matrix().reshape(6, 6), o["cov"], rtol=0, atol=POSE_TOL ** 2 + 1e-5 * np.abs(o["cov"]).max())
+    np.testing.assert_array_equal(icp.get_particle_weight(), o["weights"])
+    np.testing.assert_allclose(icp.get_particle_history().reshape(12, 6, P), o["history"], rtol=0, atol=POSE_TOL)
+    assert icp.iterations_done() == 12
+    # and the scan actually registers: mean close to the planted relative motion
+    assert np.abs(icp.get_transformation() - lidar.gt_rel)[:3].max() < 0.05
+    assert np.abs(icp.get_transformation() - lidar.gt_rel)[3:].max() < 0.005
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_vectors_through_c_abi(name):
+    """The committed outputs of the reference's own sources (tests/golden/*.npz)."""
+    g = load_golden(name)
+    I, lr, md, es, thr, K, full = g["params"]
+    prm = sv.SteinICPParam(iterations=int(I), lr=float(lr), max_dist=float(md), check_early_stop=bool(es),
+                           convergence_threshold=float(thr), KNN_count=int(K), SVN_full_grad=bool(full))
+    P = g["init_pose"].shape[1]
+    icp = sv.SVNICP(prm, g["init_pose"])
+    icp.add_cloud(g["source"], g["target"], g["init_pose"])
+    icp.set_initial_mean(g["R0"], g["t0"])
+    assert icp.stein_align() == int(g["ref_state"][0])
+    got = icp.get_particles().reshape(6, P)
+    nan_ref = np.isnan(g["ref_particles"])
+    np.testing.assert_array_equal(np.isnan(got), nan_ref)  # P == 2: bandwidth 0 -> NaN, reference behaviour
+    np.testing.assert_allclose(got, g["ref_particles"], rtol=0, atol=POSE_TOL)
+    np.testing.assert_allclose(icp.get_transformation(), g["ref_mean"], rtol=0, atol=POSE_TOL)
+    np.testing.assert_allclose(icp.get_cov_matrix().reshape(6, 6), g["ref_cov"], rtol=0, atol=1e-9 + 1e-4 * np.nanmax(np.abs(g["ref_cov"])))
+    np.testing.assert_array_equal(icp.get_particle_weight(), g["ref_weights"])
+    hist = icp.get_particle_history().reshape(int(I), 6, P)
+    np.testing.assert_allclose(hist, g["ref_history"], rtol=0, atol=POSE_TOL)
+    zero_rows = np.abs(g["ref_history"]).sum(axis=(1, 2)) == 0
+    assert (np.abs(hist).sum(axis=(1, 2)) == 0).tolist() == zero_rows.tolist()  # rows after an early stop stay zero
+    if es:
+        assert icp.iterations_done() == int((~zero_rows).sum()) + 1
+
+
+def test_single_particle_is_gauss_newton_icp(oracle, small):
+    """P == 1: stein_grad = -H^-1 b (SVNICP.cpp:88-89); recovers the planted transform."""
+    init = np.zeros((6, 1))
+    icp = sv.SVNICP(sv.SteinICPParam(iterations=8, KNN_count=20, max_dist=3.0), init)
+    icp.add_cloud(small.source, small.target, init)
+    icp.set_initial_mean(small.R0, small.t0)
+    icp.stein_align()
+    prm = orc.make_params(iterations=8, knn_count=20, max_dist=3.0)
+    o = oracle.align(prm, small.source, small.target, init, small.R0, small.t0)
+    np.testing.assert_allclose(icp.get_transformation(), o["mean"], rtol=0, atol=POSE_TOL)
+    np.testing.assert_allclose(icp.get_transformation(), small.gt_rel, rtol=0, atol=5e-3)
+
+
+def test_deterministic_and_reusable(lidar):
+    """One long-lived instance reused for several scans (OdometryPipeline.h:125); identical inputs -> identical bits."""
+    icp = make_icp(lidar, iterations=6, KNN_count=100, max_dist=3.0)
+    icp.stein_align()
+    a = icp.get_particles().copy()
+    other = synth.make_uniform_problem(64, 700, 9000, seed=9)
+    icp.add_cloud(other.source, other.target, other.init_pose)
+    icp.set_initial_mean(other.R0, other.t0)
+    icp.stein_align()
+    assert np.abs(icp.get_transformation() - other.gt_rel).max() < 0.02
+    icp.add_cloud(lidar.source, lidar.target, lidar.init_pose)
+    icp.set_initial_mean(lidar.R0, lidar.t0)
+    icp.stein_align()
+    np.testing.assert_array_equal(icp.get_particles(), a)
+
+
+def test_errors(small):
+    with pytest.raises(sv.SvnIcpError):
+        sv.SVNICP(sv.SteinICPParam(KNN_count=1000), np.zeros((6, 4)))
+    icp = sv.SVNICP(sv.SteinICPParam(iterations=1), np.zeros((6, 4)))
+    with pytest.raises(sv.SvnIcpError, match="before add_cloud"):
+        icp.stein_align()
+    with pytest.raises(sv.SvnIcpError, match="empty cloud"):
+        icp.add_cloud(np.zeros((0, 3)), small.target, np.zeros((6, 4)))
