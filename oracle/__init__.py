@@ -146,6 +146,17 @@ class Oracle:
                                  C.c_double(max_dist), _ptr(idx), _ptr(mask))
         return idx, mask
 
+    def gn_given_corr(self, R, t, R0, t0, src, tgt, corr_idx, corr_mask, max_dist):
+        R, t, src, tgt = _f64(R), _f64(t), _f64(src), _f64(tgt)
+        P = len(R)
+        corr_idx = np.ascontiguousarray(corr_idx, dtype=np.int32)
+        corr_mask = np.ascontiguousarray(corr_mask, dtype=np.uint8)
+        H = np.zeros((P, 6, 6))
+        b = np.zeros((P, 6))
+        self.lib.oracle_gn_given_corr(_ptr(R), _ptr(t), C.c_int(P), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(src), C.c_int64(len(src)),
+                                      _ptr(tgt), _ptr(corr_idx), _ptr(corr_mask), C.c_double(max_dist), _ptr(H), _ptr(b))
+        return H, b
+
     def rbf_kernel(self, x):
         x = _f64(x)
         P = len(x)

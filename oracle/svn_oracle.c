@@ -697,3 +697,49 @@ void oracle_corr_f32(const float *xf, int P, const float *sp, int64_t n_s, const
     }
   }
 }
+
+/* Newton_grad_right (SVNICP.cpp:116-164) in fp64 for GIVEN correspondences (global map index + mask per
+ * (particle, point)), so the Gauss-Newton arithmetic of the CUDA path can be checked independently of the
+ * handful of near-tie index differences between fp32 and fp64 geometry.  R,t [P][9],[P][3]. */
+void oracle_gn_given_corr(const double *R, const double *t, int P, const double R0[9], const double t0[3],
+                          const double *src, int64_t n_s, const double *tgt, const int32_t *corr_idx,
+                          const uint8_t *corr_mask, double max_dist, double *H, double *b) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int p = 0; p < P; p++) {
+    double Rt[9], tt[3], R0t[3];
+    mat3_mul(R0, R + 9 * p, Rt);
+    mat3_vec(R0, t + 3 * p, R0t);
+    for (int c = 0; c < 3; c++) tt[c] = t0[c] + R0t[c];
+    double *Hp = H + 36 * p, *bp = b + 6 * p;
+    memset(Hp, 0, 36 * sizeof(double));
+    memset(bp, 0, 6 * sizeof(double));
+    for (int64_t i = 0; i < n_s; i++) {
+      const double *s = src + 3 * i;
+      const double mu = corr_mask[(size_t)p * n_s + i] ? 1.0 : 0.0;
+      const double *m = tgt + 3 * (int64_t)corr_idx[(size_t)p * n_s + i];
+      double q[3], e[3];
+      for (int r = 0; r < 3; r++) q[r] = Rt[3 * r] * s[0] + Rt[3 * r + 1] * s[1] + Rt[3 * r + 2] * s[2] + tt[r];
+      for (int r = 0; r < 3; r++) e[r] = mu * q[r] - mu * m[r];
+      double sp[3] = {mu * s[0], mu * s[1], mu * s[2]};
+      double en = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+      double w = max_dist / (max_dist + 3.0 * en);
+      w = w * w;
+      double sh[9] = {0, -sp[2], sp[1], sp[2], 0, -sp[0], -sp[1], sp[0], 0};
+      double Rs[9], J[18];
+      mat3_mul(Rt, sh, Rs);
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) { J[6 * r + c] = Rt[3 * r + c]; J[6 * r + 3 + c] = -Rs[3 * r + c]; }
+      for (int k = 0; k < 6; k++) {
+        for (int l = 0; l < 6; l++) {
+          double acc = 0;
+          for (int r = 0; r < 3; r++) acc += J[6 * r + k] * (J[6 * r + l] * w);
+          Hp[6 * k + l] += acc;
+        }
+        double accb = 0;
+        for (int r = 0; r < 3; r++) accb += J[6 * r + k] * (w * e[r]);
+        bp[k] += accb;
+      }
+    }
+    for (int k = 0; k < 6; k++) Hp[7 * k] += 1e-6;
+  }
+}

@@ -518,7 +518,7 @@ int svnicp_align(svnicp_handle h) {
     }
 #define PROF(k) do { if (h->profile) CU(cudaEventRecord(h->prof_events[(size_t)e * 7 + (k)], st)); } while (0)
     PROF(0);
-    h->launches += launch_prep(ia, st);
+    h->launches += launch_prep(ia, st, 0);
     PROF(1);
     h->launches += launch_filter(ia, st);
     PROF(2);
@@ -544,7 +544,7 @@ int svnicp_align(svnicp_handle h) {
   h->enqueued_iters = e;
   CU(cudaEventRecord(h->ev[2], st));
   // ---- epilogue: final x, last stop decision / history row, getters (SVNICP.cpp:111, :281-308) ----
-  h->launches += launch_prep(ia, st);
+  h->launches += launch_prep(ia, st, 1);
   {
     int rc = do_allgather(h);
     if (rc) return rc;

@@ -60,7 +60,7 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // ---------------------------------------------------------------------------------------------
 // k_prep
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_prep(IterArgs a) {
+__global__ void __launch_bounds__(1024) k_prep(IterArgs a, int x_only) {
   if (a.ctrl->stop) return;
   __shared__ double s_red[32][12];
   __shared__ float s_center[12];
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(1024) k_prep(IterArgs a) {
 #pragma unroll
     for (int i = 0; i < 3; i++) { rec[REC_X + i] = t[i]; rec[REC_X + 3 + i] = w[i]; }
     rec[REC_DNORM] = a.dnorm[l];
+    if (x_only) continue;  // scan epilogue: only the final poses are needed
     // A' = R0 (R - I) R0^T, tau = R0 t   (so that q_pb - q0_b = A' (R0 s_b) + tau)
     double D[9], T[9], M[9];
 #pragma unroll
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(1024) k_prep(IterArgs a) {
       acc[9 + r] += (double)f;
     }
   }
+  if (x_only) return;
 #pragma unroll
   for (int i = 0; i < 12; i++) acc[i] = warp_sum(acc[i]);
   if (lane == 0)
@@ -451,8 +453,8 @@ void init_iter_kernels() {
   cudaFuncSetAttribute(k_gn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
-int launch_prep(const IterArgs &a, cudaStream_t st) {
-  k_prep<<<1, 1024, 0, st>>>(a);
+int launch_prep(const IterArgs &a, cudaStream_t st, int x_only) {
+  k_prep<<<1, 1024, 0, st>>>(a, x_only);
   return 1;
 }
 

@@ -53,7 +53,7 @@ struct IterArgs {
   int32_t *dbg_idx;
   uint8_t *dbg_mask;
 };
-int launch_prep(const IterArgs &a, cudaStream_t st);
+int launch_prep(const IterArgs &a, cudaStream_t st, int x_only);
 int launch_filter(const IterArgs &a, cudaStream_t st);
 int launch_gn(const IterArgs &a, cudaStream_t st);
 int launch_finalize(const IterArgs &a, cudaStream_t st);

@@ -26,7 +26,9 @@ CASES = {
     # P == 2: the lower median of {0,0,d,d} is 0 -> bandwidth 0 -> NaN translations.  Reference behaviour, kept.
     "svn_p2_lr05": (2, 200, 2000, 8, 4, 1, 0, 1e-5, 0.5, 1.0, 14),
     "svn_p3_lr05": (3, 200, 2000, 8, 4, 1, 0, 1e-5, 0.5, 1.0, 17),
-    "svn_earlystop_p8": (8, 300, 3000, 16, 40, 0, 1, 5e-4, 1.0, 3.0, 15),
+    # threshold chosen so that the stop fires mid-run (epoch 5): rows 5.. of the history stay zero
+    "svn_earlystop_p8": (8, 300, 3000, 16, 40, 0, 1, 1.5e-2, 1.0, 3.0, 15),
+    "svn_earlystop_never_p8": (8, 300, 3000, 16, 12, 1, 1, 5e-4, 1.0, 3.0, 15),
     "svn_small_map_p5": (5, 60, 10, 16, 3, 1, 0, 1e-5, 1.0, 3.0, 16),  # N_t < K: zero padded candidates
 }
 
