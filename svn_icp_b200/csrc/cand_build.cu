@@ -23,6 +23,7 @@ constexpr unsigned long long EMPTY_KEY = 0xffffffffffffffffull;
 constexpr int RING_MAX = 6;
 constexpr int KNN_WARPS = 4;
 constexpr int KNN_CAP = 1024;
+constexpr int KNN_BINS = 64;
 
 struct Ent {
   double d;
@@ -116,13 +117,13 @@ __device__ void warp_sort(Ent *buf, int n) {
   const int lane = lane_id();
   for (int k = 2; k <= n; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < n; i += 32) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const Ent a = buf[i], b = buf[ixj];
-          const bool up = (i & k) == 0;
-          if (ent_less(b, a) == up) { buf[i] = b; buf[ixj] = a; }
-        }
+      // one lane per compare-exchange PAIR (n/2 pairs), so no lane idles
+      for (int t = lane; t < (n >> 1); t += 32) {
+        const int i = (t & (j - 1)) | ((t & ~(j - 1)) << 1);
+        const int ixj = i | j;
+        const Ent a = buf[i], b = buf[ixj];
+        const bool up = (i & k) == 0;
+        if (ent_less(b, a) == up) { buf[i] = b; buf[ixj] = a; }
       }
       __syncwarp();
     }
@@ -149,11 +150,12 @@ __device__ __forceinline__ double dist2(const double q[3], const double *__restr
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 k_knn(const double *__restrict__ q0, int n_s, const double *__restrict__ tgt, int n_t, const double *__restrict__ sxyz,
       const int *__restrict__ sidx, const unsigned long long *__restrict__ keys, const int *__restrict__ starts,
-      const int *__restrict__ counts, unsigned mask, double cell, int K, float4 *__restrict__ cand, int *__restrict__ fallback_count) {
+      const int *__restrict__ counts, unsigned mask, double cell, int K, float4 *__restrict__ cand, int *__restrict__ cand_idx,
+      int *__restrict__ fallback_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   Ent *buf = reinterpret_cast<Ent *>(smem_raw) + (size_t)warp * KNN_CAP;
-  __shared__ int s_start[KNN_WARPS][32], s_excl[KNN_WARPS][33];
+  __shared__ int s_start[KNN_WARPS][32], s_excl[KNN_WARPS][33], s_hist[KNN_WARPS][KNN_BINS];
   const double inv_cell = 1.0 / cell;
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -161,7 +163,7 @@ k_knn(const double *__restrict__ q0, int n_s, const double *__restrict__ tgt, in
     const double q[3] = {q0[3 * b], q0[3 * b + 1], q0[3 * b + 2]};
     const int c0[3] = {cell_of(q[0], inv_cell), cell_of(q[1], inv_cell), cell_of(q[2], inv_cell)};
     int count = 0;
-    double tau = INFINITY;
+    double tau = INFINITY, rs2_done = 0.0;
     bool done = false;
 
     for (int r = 0; r <= RING_MAX && !done; r++) {
@@ -225,7 +227,7 @@ k_knn(const double *__restrict__ q0, int n_s, const double *__restrict__ tgt, in
       for (int i = lane; i < count; i += 32) nin += (buf[i].d < rs2) ? 1 : 0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) nin += __shfl_xor_sync(0xffffffffu, nin, o);
-      if (nin >= K) done = true;
+      if (nin >= K) { done = true; rs2_done = rs2; }
     }
 
     if (!done) {  // sparse neighbourhood (or N_t < K): exact brute-force sweep of the whole map
@@ -249,16 +251,65 @@ k_knn(const double *__restrict__ q0, int n_s, const double *__restrict__ tgt, in
         if (count + 32 > KNN_CAP) count = warp_compact(buf, count, K, &tau);
       }
     }
+    if (done) {
+      // >= K points lie inside rs2_done.  Cut the buffer down before sorting: 64-bin histogram of d over [0, rs2),
+      // keep everything up to the bin in which the K-th smallest falls (exact superset of the K nearest).
+      int *hist = s_hist[warp];
+      hist[lane] = 0;
+      hist[lane + 32] = 0;
+      __syncwarp();
+      const double scale = (double)KNN_BINS / rs2_done;
+      for (int i = lane; i < count; i += 32) {
+        const double d = buf[i].d;
+        if (d < rs2_done) atomicAdd(&hist[min(KNN_BINS - 1, (int)(d * scale))], 1);
+      }
+      __syncwarp();
+      // inclusive prefix over the 64 bins (2 per lane)
+      const int h0 = hist[2 * lane], h1 = hist[2 * lane + 1];
+      int incl = h0 + h1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int before = incl - h0 - h1;
+      int tbin = KNN_BINS;  // first bin whose inclusive count reaches K
+      if (before < K && before + h0 >= K) tbin = 2 * lane;
+      else if (before + h0 < K && incl >= K) tbin = 2 * lane + 1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tbin = min(tbin, __shfl_xor_sync(0xffffffffu, tbin, o));
+      // in-place compaction (write index never passes the read index)
+      int m_out = 0;
+      for (int i0 = 0; i0 < count; i0 += 32) {
+        const int i = i0 + lane;
+        Ent e;
+        bool keep = false;
+        if (i < count) {
+          e = buf[i];
+          keep = (e.d < rs2_done) && (min(KNN_BINS - 1, (int)(e.d * scale)) <= tbin);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) buf[m_out + __popc(m & lt_mask)] = e;
+        m_out += __popc(m);
+        __syncwarp();
+      }
+      count = m_out;
+    }
     count = warp_compact(buf, count, K, &tau);
 
-    // emit: relative fp32 coordinates m - q0 and the global map index; zero padding -> map point 0
+    // emit: relative fp32 coordinates m - q0 (w = lower bound of their norm: slots ascend in it, which k_gn's exact
+    // early exit relies on) and the global map index; zero padding -> map point 0 (knn.cu:343)
     for (int k = lane; k < K; k += 32) {
       const double *m;
       int gi;
       if (k < count) { m = sxyz + 3 * (size_t)buf[k].pos; gi = buf[k].idx; }
-      else { m = tgt; gi = 0; }  // knn.cu:343: idxs zero-initialised
-      cand[(size_t)b * K + k] = make_float4(__double2float_rn(m[0] - q[0]), __double2float_rn(m[1] - q[1]),
-                                            __double2float_rn(m[2] - q[2]), __int_as_float(gi));
+      else { m = tgt; gi = 0; }
+      const float cx = __double2float_rn(m[0] - q[0]), cy = __double2float_rn(m[1] - q[1]), cz = __double2float_rn(m[2] - q[2]);
+      const double nrm = sqrt((double)cx * cx + (double)cy * cy + (double)cz * cz);
+      const float w = (k < count) ? __double2float_rd(nrm * (1.0 - 1e-6)) : INFINITY;  // padded duplicates never need a visit
+      cand[(size_t)b * K + k] = make_float4(cx, cy, cz, w);
+      cand_idx[(size_t)b * K + k] = gi;
     }
     __syncwarp();
   }
@@ -286,7 +337,7 @@ int launch_cand_build(const CandBuildArgs &a, cudaStream_t st) {
   const int max_grid = a.sm_count * 12;
   if (grid > max_grid) grid = max_grid;
   k_knn<<<grid, KNN_WARPS * 32, knn_smem_bytes(), st>>>(a.q0, a.n_s, a.tgt64, a.n_t, a.sxyz, a.sidx, a.keys, a.starts, a.counts,
-                                                         (unsigned)(a.table_size - 1), a.cell, a.K, a.cand, a.fallback_count);
+                                                         (unsigned)(a.table_size - 1), a.cell, a.K, a.cand, a.cand_idx, a.fallback_count);
   launches++;
   return launches;
 }

@@ -90,7 +90,8 @@ struct svnicp_handle_t {
   // device buffers
   DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, rec, xs, delta, Hbar_inv, stats, particles, init_pose;
   DevBuf<float4> sp, cand, clist;
-  DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc;  // misc: [0] cursor, [1] fallback count
+  DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc, cand_idx;
+  int Kp = 100;  // misc: [0] cursor, [1] fallback count
   DevBuf<unsigned long long> keys, kept_hist;
   DevBuf<float> xf, history;
   DevBuf<unsigned> hist;
@@ -278,6 +279,7 @@ void svnicp_destroy(svnicp_handle h) {
                          &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose};
   for (auto *b : d) b->release();
   h->sp.release(); h->cand.release(); h->clist.release();
+  h->cand_idx.release();
   h->ccount.release(); h->counts.release(); h->starts.release(); h->fill.release(); h->pt_slot.release(); h->sidx.release(); h->misc.release();
   h->keys.release(); h->kept_hist.release(); h->xf.release(); h->history.release(); h->hist.release(); h->ctrl.release();
   h->dbg_idx.release(); h->dbg_mask.release();
@@ -338,13 +340,14 @@ int svnicp_init_sharding(svnicp_handle h, const void *unique_id128, int rank, in
 }
 
 static int choose_shape(svnicp_handle h) {
-  const int K = h->K;
+  const int Kp = (h->K + 3) & ~3;
+  h->Kp = Kp;
   int TB = 32;
   const int S = 3;
-  while (TB > 4 && gn_stage_bytes(TB, K) * S > 100 * 1024) TB >>= 1;
+  while (TB > 4 && gn_stage_bytes(TB, Kp) * S > 100 * 1024) TB >>= 1;
   h->TB = TB;
   h->stages = S;
-  h->gn_smem = gn_stage_bytes(TB, K) * S + 2 * S * sizeof(uint64_t) + 128;
+  h->gn_smem = gn_stage_bytes(TB, Kp) * S + 2 * S * sizeof(uint64_t) + 128;
   int PG = 1;
   while (PG < h->P_l && PG < 256) PG <<= 1;
   h->PG = PG;
@@ -373,7 +376,8 @@ int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int sou
   CU(h->q0.ensure((size_t)3 * n_s));
   CU(h->sp.ensure((size_t)n_pad + 64));
   CU(h->cand.ensure((size_t)n_s * h->K));
-  CU(h->clist.ensure((size_t)n_pad * h->K));
+  CU(h->cand_idx.ensure((size_t)n_s * h->K));
+  CU(h->clist.ensure((size_t)n_pad * h->Kp));
   CU(h->ccount.ensure((size_t)n_pad + 64));
   CU(cudaMemsetAsync(h->ccount.p, 0, ((size_t)n_pad + 64) * sizeof(int), h->stream));
   size_t table = 1024;
@@ -472,7 +476,7 @@ int svnicp_align(svnicp_handle h) {
   size_t table = 1024;
   while (table < (size_t)2 * h->n_t) table <<= 1;
   cb.table_size = (int)table;
-  cb.sxyz = h->sxyz.p; cb.sidx = h->sidx.p; cb.cand = h->cand.p;
+  cb.sxyz = h->sxyz.p; cb.sidx = h->sidx.p; cb.cand = h->cand.p; cb.cand_idx = h->cand_idx.p;
   cb.sm_count = h->sm_count;
   h->launches += launch_cand_build(cb, st);
   CU(cudaGetLastError());
@@ -480,7 +484,7 @@ int svnicp_align(svnicp_handle h) {
 
   IterArgs ia;
   memset(&ia, 0, sizeof(ia));
-  ia.n_s = (int)h->n_s; ia.n_pad = h->n_pad; ia.K = h->K;
+  ia.n_s = (int)h->n_s; ia.n_pad = h->n_pad; ia.K = h->K; ia.Kp = h->Kp; ia.cand_idx = h->cand_idx.p;
   ia.P = h->P; ia.p_lo = h->p_lo; ia.P_l = h->P_l;
   ia.sc = h->sc;
   ia.max_dist = (float)h->max_dist;
@@ -674,11 +678,11 @@ int svnicp_get_candidates(svnicp_handle h, int32_t *out_idx, float *out_rel) {
   if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
   CU(cudaSetDevice(h->device));
   const size_t n = (size_t)h->n_s * h->K;
-  std::vector<float4> tmp(n);
-  CU(cudaMemcpy(tmp.data(), h->cand.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < n; i++) {
-    if (out_idx) memcpy(&out_idx[i], &tmp[i].w, 4);
-    if (out_rel) { out_rel[3 * i] = tmp[i].x; out_rel[3 * i + 1] = tmp[i].y; out_rel[3 * i + 2] = tmp[i].z; }
+  if (out_idx) CU(cudaMemcpy(out_idx, h->cand_idx.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (out_rel) {
+    std::vector<float4> tmp(n);
+    CU(cudaMemcpy(tmp.data(), h->cand.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) { out_rel[3 * i] = tmp[i].x; out_rel[3 * i + 1] = tmp[i].y; out_rel[3 * i + 2] = tmp[i].z; }
   }
   return SVNICP_OK;
 }

@@ -29,6 +29,9 @@ constexpr int NACC = 16;  // W, S1(3), S2(6: xx xy xz yy yz zz), E(3), C(3)
 constexpr int MED_PASSES = 5;  // 11 + 13 + 13 + 13 + 13 = 63 key bits
 constexpr int MED_BINS = 8192;
 
+constexpr int PRUNE_BINS = 64;        // range bins of the pruning-radius envelope
+constexpr double PRUNE_BIN_W = 2.0;   // metres per bin (points beyond PRUNE_BINS*PRUNE_BIN_W use alpha*|s|+beta)
+
 struct Ctrl {
   int stop;         // 1 once the early stop fired (all later kernels return immediately)
   int iter;         // iterations whose pose update has been applied
@@ -40,6 +43,7 @@ struct Ctrl {
   float taubar[3];
   float alpha;
   float beta;
+  float env[PRUNE_BINS];  // env[i] >= max_p (sigma_p r + beta_p) for every r <= (i+1)*PRUNE_BIN_W
   // median radix select (lower median of P^2 pairwise squared distances, SVNICP.cpp:262)
   unsigned long long sel_prefix[MED_PASSES + 1];
   unsigned long long sel_rank[MED_PASSES + 1];

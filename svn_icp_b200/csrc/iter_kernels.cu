@@ -57,6 +57,29 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// largest eigenvalue of M^T M (M 3x3 row-major) = sigma_max(M)^2, rounded up; NaN propagates
+__device__ inline double sym3_max_eig_MtM(const double M[9]) {
+  double B[6];  // 00 01 02 11 12 22
+  B[0] = M[0] * M[0] + M[3] * M[3] + M[6] * M[6];
+  B[1] = M[0] * M[1] + M[3] * M[4] + M[6] * M[7];
+  B[2] = M[0] * M[2] + M[3] * M[5] + M[6] * M[8];
+  B[3] = M[1] * M[1] + M[4] * M[4] + M[7] * M[7];
+  B[4] = M[1] * M[2] + M[4] * M[5] + M[7] * M[8];
+  B[5] = M[2] * M[2] + M[5] * M[5] + M[8] * M[8];
+  const double tr = B[0] + B[3] + B[5];
+  const double q = tr / 3.0;
+  const double p1 = B[1] * B[1] + B[2] * B[2] + B[4] * B[4];
+  const double p2 = (B[0] - q) * (B[0] - q) + (B[3] - q) * (B[3] - q) + (B[5] - q) * (B[5] - q) + 2.0 * p1;
+  const double p = sqrt(p2 / 6.0);
+  if (!(p > 1e-300)) return (tr != tr) ? tr : q * (1.0 + 1e-9);
+  const double c00 = (B[0] - q) / p, c11 = (B[3] - q) / p, c22 = (B[5] - q) / p, c01 = B[1] / p, c02 = B[2] / p, c12 = B[4] / p;
+  double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+  r = fmin(fmax(r, -1.0), 1.0);
+  const double lam = q + 2.0 * p * cos(acos(r) / 3.0);
+  // never above the Frobenius bound (= trace), never optimistic: 1e-9 relative + absolute guard for rounding
+  return fmin(tr, lam * (1.0 + 1e-9) + 1e-30) * (tr == tr ? 1.0 : NAN);
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_prep
 // ---------------------------------------------------------------------------------------------
@@ -65,6 +88,8 @@ __global__ void __launch_bounds__(1024) k_prep(IterArgs a, int x_only) {
   __shared__ double s_red[32][12];
   __shared__ float s_center[12];
   __shared__ double s_max[32][2];
+  __shared__ int s_env[PRUNE_BINS];
+  __shared__ int s_nan;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double *R0 = a.sc.R0;
   double acc[12];
@@ -118,17 +143,29 @@ __global__ void __launch_bounds__(1024) k_prep(IterArgs a, int x_only) {
     s_center[tid] = __double2float_rn(s / (double)a.P_l);
   }
   __syncthreads();
+  for (int i = tid; i < PRUNE_BINS; i += blockDim.x) s_env[i] = 0;
+  __syncthreads();
   double ma = 0.0, mb = 0.0;
   for (int l = tid; l < a.P_l; l += blockDim.x) {
     const float *xf = a.xf + (size_t)l * 12;
-    double da = 0, db = 0;
+    double M[9], db = 0;
 #pragma unroll
-    for (int i = 0; i < 9; i++) { const double d = (double)xf[i] - (double)s_center[i]; da += d * d; }
+    for (int i = 0; i < 9; i++) M[i] = (double)xf[i] - (double)s_center[i];
 #pragma unroll
     for (int i = 9; i < 12; i++) { const double d = (double)xf[i] - (double)s_center[i]; db += d * d; }
+    // |(A_p - Abar) s| <= sigma_max(A_p - Abar) |s|: largest eigenvalue of M^T M (trigonometric closed form)
+    double da = sym3_max_eig_MtM(M);
     // NaN state (e.g. the reference's P == 2 bandwidth-0 quirk) must poison the radius, not vanish in fmax
     ma = (da != da) ? da : fmax(ma, da);
     mb = (db != db) ? db : fmax(mb, db);
+    // per-range-bin envelope max_p (sigma_p r + beta_p) at the bin's upper edge r (tighter than max sigma * r + max beta)
+    if (da == da && db == db) {
+      const double sg = sqrt(da) * (1.0 + 1e-6), bt = sqrt(db) * (1.0 + 1e-6);
+      for (int i = 0; i < PRUNE_BINS; i++) {
+        const float v = __double2float_ru(sg * ((double)(i + 1) * PRUNE_BIN_W) + bt);
+        atomicMax(&s_env[i], __float_as_int(v));  // non-negative floats order like their bit patterns
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -150,11 +187,14 @@ __global__ void __launch_bounds__(1024) k_prep(IterArgs a, int x_only) {
     c->alpha = __double2float_ru(sqrt(fa) * (1.0 + 1e-6));
     c->beta = __double2float_ru(sqrt(fb) * (1.0 + 1e-6));
     c->kept_total = 0ull;
+    s_nan = (fa != fa || fb != fb) ? 1 : 0;
   }
+  __syncthreads();
+  for (int i = tid; i < PRUNE_BINS; i += blockDim.x) a.ctrl->env[i] = s_nan ? NAN : __int_as_float(s_env[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_filter: exact candidate pruning, one warp per source point
+// k_filter: exact candidate pruning, one warp per source point (the HBM-streaming kernel)
 // ---------------------------------------------------------------------------------------------
 constexpr float PRUNE_MARGIN = 1e-4f;  // metres; absorbs every fp32 rounding in q, qbar and the norms
 
@@ -170,7 +210,7 @@ __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
 #pragma unroll
   for (int i = 0; i < 3; i++) tb[i] = c->taubar[i];
   const float alpha = c->alpha, beta = c->beta;
-  const int K = a.K;
+  const int K = a.K, Kp = a.Kp;
   const unsigned lt = (1u << lane) - 1u;
   unsigned long long kept = 0;
   for (int b = gw; b < a.n_s; b += nw) {
@@ -178,7 +218,11 @@ __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
     const float qx = fmaf(A[0], s.x, fmaf(A[1], s.y, fmaf(A[2], s.z, tb[0])));
     const float qy = fmaf(A[3], s.x, fmaf(A[4], s.y, fmaf(A[5], s.z, tb[1])));
     const float qz = fmaf(A[6], s.x, fmaf(A[7], s.y, fmaf(A[8], s.z, tb[2])));
-    const float rho = fmaf(alpha, s.w, beta);
+    // radius of the ball that holds every particle's query for this point: the per-range-bin envelope where it
+    // applies, never worse than sigma_max * |s| + beta_max
+    float rho = fmaf(alpha, s.w, beta);
+    const int rbin = (int)(s.w * (float)(1.0 / PRUNE_BIN_W));
+    if (rbin < PRUNE_BINS) rho = fminf(rho, c->env[rbin]);  // fminf: a NaN env entry leaves rho (itself NaN then) alone
     const float4 *row = a.cand + (size_t)b * K;
     float4 e[NCH];
     float d2[NCH];
@@ -187,7 +231,7 @@ __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
     for (int ch = 0; ch < NCH; ch++) {
       const int k = ch * 32 + lane;
       if (k < K) {
-        e[ch] = row[k];
+        e[ch] = __ldcs(row + k);  // streamed once per iteration: do not keep in L2
         const float dx = qx - e[ch].x, dy = qy - e[ch].y, dz = qz - e[ch].z;
         d2[ch] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
         dmin = fminf(dmin, d2[ch]);  // fminf drops NaN: a NaN d2 never becomes the minimum
@@ -200,7 +244,7 @@ __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
     // nearest neighbour of a query within rho of it
     const float lim = sqrtf(dmin) + 2.0f * rho + PRUNE_MARGIN;
     const float thr = lim * lim * (1.0f + 1e-5f);
-    float4 *out = a.clist + (size_t)b * K;
+    float4 *out = a.clist + (size_t)b * Kp;
     int base = 0;
 #pragma unroll
     for (int ch = 0; ch < NCH; ch++) {
@@ -210,7 +254,10 @@ __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
       if (keep) out[base + __popc(m & lt)] = e[ch];
       base += __popc(m);
     }
-    if (lane == 0) { a.ccount[b] = base; kept += (unsigned long long)base; }
+    // pad to a multiple of 4 with sentinels that can never win (d = inf, strict '<') so k_gn scans in chunks of 4
+    const int padded = (base + 3) & ~3;
+    if (lane < padded - base) out[base + lane] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    if (lane == 0) { a.ccount[b] = padded; kept += (unsigned long long)base; }
   }
   if (lane == 0 && kept) atomicAdd(&a.ctrl->kept_total, kept);
 }
@@ -220,14 +267,26 @@ __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
 // ---------------------------------------------------------------------------------------------
 constexpr int GN_CONSUMERS = 256;
 constexpr int GN_THREADS = GN_CONSUMERS + 32;
-constexpr int GN_FLUSH_ROWS = 16;
+constexpr int GN_FLUSH_ROWS = 32;
 
-template <bool DBG>
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU; feeds only the robust weight and the exit bound
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// UNI: every lane of a warp works on the same source point (PG >= 32) -> the early exit is a warp vote.
+template <bool DBG, bool UNI>
 __global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {
   if (a.ctrl->stop) return;
   extern __shared__ __align__(128) unsigned char smem[];
-  const int TB = a.TB, K = a.K, S = a.stages;
-  const size_t stage_bytes = gn_stage_bytes(TB, K);
+  const int TB = a.TB, Kp = a.Kp, S = a.stages;
+  const size_t stage_bytes = gn_stage_bytes(TB, Kp);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_bytes);
   uint64_t *empty = full + S;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -256,10 +315,10 @@ __global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {
       total += TB * 16 + TB * 4;
       if (lane == 0) mbar_expect_tx(full + s, (uint32_t)total);
       __syncwarp();
-      if (lane < TB && cnt > 0) bulk_g2s(st + (size_t)lane * K * 16, a.clist + (size_t)(row0 + lane) * K, (uint32_t)bytes, full + s);
+      if (lane < TB && cnt > 0) bulk_g2s(st + (size_t)lane * Kp * 16, a.clist + (size_t)(row0 + lane) * Kp, (uint32_t)bytes, full + s);
       if (lane == 0) {
-        bulk_g2s(st + (size_t)TB * K * 16, a.sp + row0, (uint32_t)(TB * 16), full + s);
-        bulk_g2s(st + (size_t)TB * K * 16 + (size_t)TB * 16, a.ccount + row0, (uint32_t)(TB * 4), full + s);
+        bulk_g2s(st + (size_t)TB * Kp * 16, a.sp + row0, (uint32_t)(TB * 16), full + s);
+        bulk_g2s(st + (size_t)TB * Kp * 16 + (size_t)TB * 16, a.ccount + row0, (uint32_t)(TB * 4), full + s);
       }
     }
     return;
@@ -282,73 +341,92 @@ __global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {
 #pragma unroll
   for (int i = 0; i < NACC; i++) { acc[i] = 0.f; dacc[i] = 0.0; }
   int rows_in_acc = 0;
+  const int row_step = RG * Kp;
+
+// one candidate: fixed operation order (index parity with oracle_corr_f32); strict '<', first slot wins (mink.cuh:141)
+#define SVN_EVAL(C, SLOT)                                                                              \
+  {                                                                                                    \
+    const float dx_ = __fsub_rn(qx, (C).x), dy_ = __fsub_rn(qy, (C).y), dz_ = __fsub_rn(qz, (C).z);    \
+    const float d_ = __fmaf_rn(dz_, dz_, __fmaf_rn(dy_, dy_, __fmul_rn(dx_, dx_)));                    \
+    if (d_ < best) { best = d_; bi = (SLOT); }                                                         \
+  }
 
   for (int i = 0; i < n_my; i++) {
     const int s = i % S, k = i / S;
     mbar_wait(full + s, (uint32_t)(k & 1));
     const unsigned char *st = smem + (size_t)s * stage_bytes;
-    const float4 *ent = reinterpret_cast<const float4 *>(st);
-    const float4 *src = reinterpret_cast<const float4 *>(st + (size_t)TB * K * 16);
-    const int *cnt = reinterpret_cast<const int *>(st + (size_t)TB * K * 16 + (size_t)TB * 16);
-    if (active) {
-      for (int r = rg; r < TB; r += RG) {
-        const int n = cnt[r];
-        if (n == 0) continue;  // padding row
-        const float4 sv = src[r];
-        // a = A' s' ; q = a + tau : query relative to q0_b.  Order fixed (index parity).
-        const float ax = __fmaf_rn(A0, sv.x, __fmaf_rn(A1, sv.y, __fmul_rn(A2, sv.z)));
-        const float ay = __fmaf_rn(A3, sv.x, __fmaf_rn(A4, sv.y, __fmul_rn(A5, sv.z)));
-        const float az = __fmaf_rn(A6, sv.x, __fmaf_rn(A7, sv.y, __fmul_rn(A8, sv.z)));
-        const float qx = __fadd_rn(ax, t0), qy = __fadd_rn(ay, t1), qz = __fadd_rn(az, t2);
-        const float4 *e = ent + (size_t)r * K;
-        float best = INFINITY;
-        int bi = 0;
-        int kk = 0;
-        for (; kk + 4 <= n; kk += 4) {
-          float4 c[4];
-          float d[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) c[u] = e[kk + u];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const float dx = __fsub_rn(qx, c[u].x), dy = __fsub_rn(qy, c[u].y), dz = __fsub_rn(qz, c[u].z);
-            d[u] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    const float4 *src = reinterpret_cast<const float4 *>(st + (size_t)TB * Kp * 16);
+    const int *cnt = reinterpret_cast<const int *>(st + (size_t)TB * Kp * 16 + (size_t)TB * 16);
+    if (UNI || active) {
+      const float4 *e = reinterpret_cast<const float4 *>(st) + (size_t)rg * Kp;
+      int n = cnt[rg];  // padded to a multiple of 4; 0 = padding row
+      float4 sv = src[rg];
+      for (int r = rg; r < TB; r += RG, e += row_step) {
+        // software prefetch of the next row's header
+        int n_nx = 0;
+        float4 sv_nx = sv;
+        if (r + RG < TB) { n_nx = cnt[r + RG]; sv_nx = src[r + RG]; }
+        if (n != 0) {
+          float4 c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
+          // a = A' s' ; q = a + tau : query relative to q0_b.  Order fixed (index parity).
+          const float ax = __fmaf_rn(A0, sv.x, __fmaf_rn(A1, sv.y, __fmul_rn(A2, sv.z)));
+          const float ay = __fmaf_rn(A3, sv.x, __fmaf_rn(A4, sv.y, __fmul_rn(A5, sv.z)));
+          const float az = __fmaf_rn(A6, sv.x, __fmaf_rn(A7, sv.y, __fmul_rn(A8, sv.z)));
+          const float qx = __fadd_rn(ax, t0), qy = __fadd_rn(ay, t1), qz = __fadd_rn(az, t2);
+          float best = INFINITY;
+          int bi = 0;
+          SVN_EVAL(c0, 0) SVN_EVAL(c1, 1) SVN_EVAL(c2, 2) SVN_EVAL(c3, 3)
+          if (n > 4) {
+            // upper bound of |q| (distance of this particle's query from the initial-guess query q0_b)
+            const float qn = fmaf(sqrt_approx(fmaf(qz, qz, fmaf(qy, qy, qx * qx))), 1.00001f, 1e-7f);
+            for (int k0 = 4; k0 < n; k0 += 4) {
+              c0 = e[k0]; c1 = e[k0 + 1]; c2 = e[k0 + 2]; c3 = e[k0 + 3];
+              // exact early exit: slots ascend in |c| (= c.w, a lower bound) and |q - c| >= |c| - |q|, so once
+              // (|c| - |q|)^2 > best no later slot can win or tie.  NaN anywhere compares false -> no exit.
+              const float tt = c0.w - qn;
+              const bool done = (tt > 0.f) && (tt * tt * 0.99999f > best);
+              if (UNI) { if (__all_sync(0xffffffffu, done)) break; }
+              else { if (done) break; }
+              SVN_EVAL(c0, k0) SVN_EVAL(c1, k0 + 1) SVN_EVAL(c2, k0 + 2) SVN_EVAL(c3, k0 + 3)
+            }
           }
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-            if (d[u] < best) { best = d[u]; bi = kk + u; }  // strict '<', first slot wins (mink.cuh:141)
+          const float4 cw = e[bi];
+          const float ex = __fsub_rn(qx, cw.x), ey = __fsub_rn(qy, cw.y), ez = __fsub_rn(qz, cw.z);
+          const bool valid = best < Dm;  // SVGDICP.cpp:332: squared distance vs un-squared max_dist (Q1)
+          if (DBG) {
+            if (active) {
+              // recover the slot of the winner in the un-pruned table (first slot with identical coordinates)
+              const int row = (slice + i * n_slices) * TB + r;
+              const float4 *full_row = a.cand + (size_t)row * a.K;
+              int slot = 0;
+              for (int kk = 0; kk < a.K; kk++) {
+                const float4 f = full_row[kk];
+                if (f.x == cw.x && f.y == cw.y && f.z == cw.z) { slot = kk; break; }
+              }
+              a.dbg_idx[(size_t)l * a.n_s + row] = a.cand_idx[(size_t)row * a.K + slot];
+              a.dbg_mask[(size_t)l * a.n_s + row] = valid ? 1 : 0;
+            }
+          }
+          // rho = (D / (D + 3 |e|))^2  (SVNICP.cpp:120-122); masked pairs: rho' = 0 and +1 on the translation block (Q2)
+          const float en = sqrt_approx(best);
+          const float wq = Dm * rcp_approx(fmaf(3.0f, en, Dm));
+          const float rho = wq * wq;
+          const float rp = valid ? rho : 0.0f;
+          acc[0] += valid ? rho : 1.0f;
+          const float gx = rp * sv.x, gy = rp * sv.y, gz = rp * sv.z;
+          acc[1] += gx; acc[2] += gy; acc[3] += gz;
+          acc[4] = fmaf(gx, sv.x, acc[4]); acc[5] = fmaf(gx, sv.y, acc[5]); acc[6] = fmaf(gx, sv.z, acc[6]);
+          acc[7] = fmaf(gy, sv.y, acc[7]); acc[8] = fmaf(gy, sv.z, acc[8]); acc[9] = fmaf(gz, sv.z, acc[9]);
+          const float fx = rp * ex, fy = rp * ey, fz = rp * ez;  // multiplication (not select): NaN must propagate
+          acc[10] += fx; acc[11] += fy; acc[12] += fz;
+          const float wx = ax + sv.x, wy = ay + sv.y, wz = az + sv.z;  // R~ s in the world-oriented frame
+          acc[13] = fmaf(wy, fz, fmaf(-wz, fy, acc[13]));
+          acc[14] = fmaf(wz, fx, fmaf(-wx, fz, acc[14]));
+          acc[15] = fmaf(wx, fy, fmaf(-wy, fx, acc[15]));
+          rows_in_acc++;
         }
-        for (; kk < n; kk++) {
-          const float4 c = e[kk];
-          const float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
-          const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-          if (d < best) { best = d; bi = kk; }
-        }
-        const float4 cw = e[bi];
-        const float ex = __fsub_rn(qx, cw.x), ey = __fsub_rn(qy, cw.y), ez = __fsub_rn(qz, cw.z);
-        const bool valid = best < Dm;  // SVGDICP.cpp:332: squared distance vs un-squared max_dist (Q1)
-        if (DBG) {
-          const int row = (slice + i * n_slices) * TB + r;
-          a.dbg_idx[(size_t)l * a.n_s + row] = __float_as_int(cw.w);
-          a.dbg_mask[(size_t)l * a.n_s + row] = valid ? 1 : 0;
-        }
-        // rho = (D / (D + 3 |e|))^2  (SVNICP.cpp:120-122); masked pairs: rho' = 0 and +1 on the translation block (Q2)
-        const float en = sqrtf(best);
-        const float wq = __fdividef(Dm, fmaf(3.0f, en, Dm));
-        const float rho = wq * wq;
-        const float rp = valid ? rho : 0.0f;
-        acc[0] += valid ? rho : 1.0f;
-        const float gx = rp * sv.x, gy = rp * sv.y, gz = rp * sv.z;
-        acc[1] += gx; acc[2] += gy; acc[3] += gz;
-        acc[4] = fmaf(gx, sv.x, acc[4]); acc[5] = fmaf(gx, sv.y, acc[5]); acc[6] = fmaf(gx, sv.z, acc[6]);
-        acc[7] = fmaf(gy, sv.y, acc[7]); acc[8] = fmaf(gy, sv.z, acc[8]); acc[9] = fmaf(gz, sv.z, acc[9]);
-        const float fx = rp * ex, fy = rp * ey, fz = rp * ez;  // multiplication (not select): NaN must propagate
-        acc[10] += fx; acc[11] += fy; acc[12] += fz;
-        const float wx = ax + sv.x, wy = ay + sv.y, wz = az + sv.z;  // R~ s in the world-oriented frame
-        acc[13] = fmaf(wy, fz, fmaf(-wz, fy, acc[13]));
-        acc[14] = fmaf(wz, fx, fmaf(-wx, fz, acc[14]));
-        acc[15] = fmaf(wx, fy, fmaf(-wy, fx, acc[15]));
-        rows_in_acc++;
+        n = n_nx;
+        sv = sv_nx;
       }
       if (rows_in_acc >= GN_FLUSH_ROWS) {
 #pragma unroll
@@ -359,6 +437,7 @@ __global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);
   }
+#undef SVN_EVAL
   if (active) {
     double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + l) * NACC;
 #pragma unroll
@@ -449,8 +528,10 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a) {
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 void init_iter_kernels() {
-  cudaFuncSetAttribute(k_gn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_gn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_gn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_gn<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_gn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_gn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 int launch_prep(const IterArgs &a, cudaStream_t st, int x_only) {
@@ -479,8 +560,14 @@ int launch_filter(const IterArgs &a, cudaStream_t st) {
 
 int launch_gn(const IterArgs &a, cudaStream_t st) {
   dim3 grid(a.n_slices, a.n_pgroups);
-  if (a.dbg_idx) k_gn<true><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
-  else k_gn<false><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
+  const bool uni = a.PG >= 32;
+  if (a.dbg_idx) {
+    if (uni) k_gn<true, true><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
+    else k_gn<true, false><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
+  } else {
+    if (uni) k_gn<false, true><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
+    else k_gn<false, false><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
+  }
   return 1;
 }
 

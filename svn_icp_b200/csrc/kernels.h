@@ -19,7 +19,8 @@ struct CandBuildArgs {
   int table_size;  // power of two >= 2*n_t
   double *sxyz;    // [n_t][3] cell-sorted map
   int *sidx;       // [n_t] original indices
-  float4 *cand;    // [n_s][K]
+  float4 *cand;    // [n_s][K]  (m - q0 in fp32, w = lower bound of |m - q0|)
+  int *cand_idx;   // [n_s][K]  global map index per slot
   int *fallback_count;
   int sm_count;
 };
@@ -29,6 +30,8 @@ size_t knn_smem_bytes();
 struct IterArgs {
   // sizes
   int n_s, n_pad, K;
+  int Kp;           // K rounded up to a multiple of 4: row stride of the pruned lists
+  const int *cand_idx;  // [n_s][K] global map index per candidate slot (debug taps only)
   int P;            // all particles
   int p_lo, P_l;    // local slice
   // geometry

@@ -88,28 +88,35 @@ __global__ void __launch_bounds__(1024) k_decide(SteinArgs a, int epilogue) {
 // derive (prefix, rank) after pass s-1 from its histogram; every CTA computes the same values
 __device__ void select_from_hist(const unsigned *hist, unsigned long long prefix_in, unsigned long long rank_in, int nbins, int bits,
                                  unsigned long long *prefix_out, unsigned long long *rank_out) {
-  __shared__ unsigned long long s_chunk[1024];
+  // parallel: every thread sums its own run of bins, a block-wide exclusive scan of the run sums locates the run
+  // that contains the rank, and only that thread walks its (<= 32, cache-hot) bins.
+  __shared__ unsigned long long s_warp[32];
   __shared__ unsigned long long s_res[2];
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int per = (nbins + nt - 1) / nt;
   unsigned long long loc = 0;
   for (int i = 0; i < per; i++) {
     const int b = tid * per + i;
     if (b < nbins) loc += hist[b];
   }
-  s_chunk[tid] = loc;
+  unsigned long long incl = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  if (tid == 0) { s_res[0] = (prefix_in << bits) | (unsigned long long)(nbins - 1); s_res[1] = 0ull; }
   __syncthreads();
-  if (tid == 0) {
-    unsigned long long cum = 0;
-    int chunk = 0;
-    for (; chunk < nt; chunk++) {
-      if (cum + s_chunk[chunk] > rank_in) break;
-      cum += s_chunk[chunk];
-    }
-    int b = chunk * per;
+  unsigned long long wbase = 0;
+  for (int w = 0; w < warp; w++) wbase += s_warp[w];
+  const unsigned long long excl = wbase + incl - loc;
+  if (loc > 0 && excl <= rank_in && rank_in < excl + loc) {  // exactly one thread owns the rank
+    unsigned long long cum = excl;
+    int b = tid * per;
     for (;; b++) {
-      const unsigned long long h = (b < nbins) ? hist[b] : 0ull;
-      if (cum + h > rank_in || b >= nbins - 1) break;
+      const unsigned long long h = hist[b];
+      if (cum + h > rank_in) break;
       cum += h;
     }
     s_res[0] = (prefix_in << bits) | (unsigned long long)b;
@@ -179,12 +186,13 @@ __device__ double finish_bandwidth(const SteinArgs &a) {
 // records of 32 particles j are staged in shared memory per step; lane = j.
 // ---------------------------------------------------------------------------------------------
 constexpr int ST_WARPS = 8;
-constexpr int ST_TJ = 32;
+constexpr int ST_TJ = 32;    // j-tile of the pre-conditioned SVGD kernel
+constexpr int ST_TJF = 128;  // j-tile of the full SVN kernel (4 j per lane per tile)
 
 __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_full(SteinArgs a) {
   Ctrl *c = a.ctrl;
   if (c->stop) return;
-  __shared__ double s_rec[33][ST_TJ + 1];
+  __shared__ double s_rec[33][ST_TJF + 1];
   const double h = finish_bandwidth(a);
   if (blockIdx.x == 0 && threadIdx.x == 0) c->bandwidth = h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -200,29 +208,35 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_full(SteinArgs a) {
 #pragma unroll
   for (int q = 0; q < 6; q++) v[q] = 0.0;
   const double two_over_h = 2.0 / h;
-  for (int j0 = 0; j0 < a.P; j0 += ST_TJ) {
+  for (int j0 = 0; j0 < a.P; j0 += ST_TJF) {
     __syncthreads();
-    for (int e = tid; e < 33 * ST_TJ; e += blockDim.x) {
+    for (int e = tid; e < 33 * ST_TJF; e += blockDim.x) {
       const int jj = e / 33, q = e % 33;
       s_rec[q][jj] = (j0 + jj < a.P) ? a.rec[(size_t)(j0 + jj) * REC + q] : 0.0;
     }
     __syncthreads();
-    if (active && j0 + lane < a.P) {
-      double dl[6], D = 0.0;
+    if (active) {
+      // lane handles j = j0 + lane, +32, +64, +96 (fixed order: the N-GPU run sums in the same order)
+#pragma unroll 2
+      for (int u = 0; u < ST_TJF / 32; u++) {
+        const int jj = u * 32 + lane;
+        if (j0 + jj >= a.P) break;
+        double dl[6], D = 0.0;
 #pragma unroll
-      for (int d = 0; d < 6; d++) { dl[d] = xi[d] - s_rec[REC_X + d][lane]; D += dl[d] * dl[d]; }
-      const double kij = exp(-D / h);          // :264
-      const double k2 = kij * kij;             // :238
-      double g[6];
+        for (int d = 0; d < 6; d++) { dl[d] = xi[d] - s_rec[REC_X + d][jj]; D += dl[d] * dl[d]; }
+        const double kij = exp(-D / h);          // :264
+        const double k2 = kij * kij;             // :238
+        double g[6];
 #pragma unroll
-      for (int d = 0; d < 6; d++) g[d] = two_over_h * (dl[d] * kij);  // :233
-      int q = 0;
+        for (int d = 0; d < 6; d++) g[d] = two_over_h * (dl[d] * kij);  // :233
+        int q = 0;
 #pragma unroll
-      for (int r = 0; r < 6; r++)
+        for (int r = 0; r < 6; r++)
 #pragma unroll
-        for (int cc = r; cc < 6; cc++, q++) Hm[q] += k2 * s_rec[REC_H + q][lane] + g[r] * g[cc];  // :236-242
+          for (int cc = r; cc < 6; cc++, q++) Hm[q] += k2 * s_rec[REC_H + q][jj] + g[r] * g[cc];  // :236-242
 #pragma unroll
-      for (int d = 0; d < 6; d++) v[d] += g[d] - kij * s_rec[REC_B + d][lane];  // :244 with b' = -b
+        for (int d = 0; d < 6; d++) v[d] += g[d] - kij * s_rec[REC_B + d][jj];  // :244 with b' = -b
+      }
     }
   }
 #pragma unroll

@@ -212,6 +212,65 @@ def make_problem(P: int, sensor: str = "64", scan_index: int = 8, n_map_scans: i
                        np.r_[trel, rotvec_from_rot(Rrel)], Rg, tg)
 
 
+def saturated_map(world: World, centre: np.ndarray, map_range: float, rng: np.random.Generator, voxel: float = 1.0,
+                  cap: int = 20, density: float = 40.0, noise: float = 0.02) -> np.ndarray:
+    """Local map of a region that has been driven through: every surface voxel within map_range holds `cap` points
+    (what the reference's VoxelHashMap converges to, VoxelHashMap.cpp:22-41).  Surfaces are sampled directly
+    (ground, walls, box faces, cylinder mantles) at `density` points / m^2, then capped per voxel."""
+    cx, cy = centre[0], centre[1]
+    x0, x1 = cx - map_range, cx + map_range
+    parts = []
+
+    def plane(n, ax_u, lo_u, hi_u, ax_v, lo_v, hi_v, ax_w, w):
+        p = np.empty((n, 3))
+        p[:, ax_u] = rng.uniform(lo_u, hi_u, n)
+        p[:, ax_v] = rng.uniform(lo_v, hi_v, n)
+        p[:, ax_w] = w
+        return p
+
+    wy = world.wall_y
+    parts.append(plane(int(density * (x1 - x0) * 2 * wy), 0, x0, x1, 1, -wy, wy, 2, 0.0))
+    for s in (-wy, wy):
+        parts.append(plane(int(density * (x1 - x0) * world.wall_h), 0, x0, x1, 2, 0.0, world.wall_h, 1, s))
+    for lo, hi in zip(world.boxes_lo, world.boxes_hi):
+        if hi[0] < x0 or lo[0] > x1:
+            continue
+        d = hi - lo
+        parts.append(plane(int(density * d[0] * d[1]) + 1, 0, lo[0], hi[0], 1, lo[1], hi[1], 2, hi[2]))
+        for s in (lo[0], hi[0]):
+            parts.append(plane(int(density * d[1] * d[2]) + 1, 1, lo[1], hi[1], 2, lo[2], hi[2], 0, s))
+        for s in (lo[1], hi[1]):
+            parts.append(plane(int(density * d[0] * d[2]) + 1, 0, lo[0], hi[0], 2, lo[2], hi[2], 1, s))
+    for c, r, h in zip(world.cyl_c, world.cyl_r, world.cyl_h):
+        if c[0] + r < x0 or c[0] - r > x1:
+            continue
+        n = int(density * 2 * np.pi * r * h) + 1
+        a = rng.uniform(0, 2 * np.pi, n)
+        parts.append(np.stack([c[0] + r * np.cos(a), c[1] + r * np.sin(a), rng.uniform(0, h, n)], 1))
+    pts = np.concatenate(parts)
+    pts = pts + rng.normal(0.0, noise, pts.shape)
+    pts = pts[np.linalg.norm(pts - np.asarray(centre), axis=1) < map_range]
+    pts = pts[rng.permutation(len(pts))]
+    return voxel_cap(pts, voxel, cap)
+
+
+def make_problem_saturated(P: int, sensor: str = "64", scan_index: int = 8, seed: int = 0xC0FFEE, map_range: float = 100.0,
+                           voxel: float = 1.0, map_cap: int = 20, world: World | None = None) -> ScanProblem:
+    """BASELINE.json configs[1]/[2] workload: raw scan (~120k / ~260k points) against a saturated voxel-hash local map."""
+    world = world or make_world(seed)
+    rng = np.random.default_rng(seed ^ 0xBEEF ^ scan_index)
+    src, (Rg, tg) = make_scan(world, scan_index, sensor, seed)
+    target = saturated_map(world, tg, map_range, rng, voxel, map_cap)
+    target = target[rng.permutation(len(target))]
+    pert = rng.normal(0.0, [0.05, 0.05, 0.02, 0.002, 0.002, 0.002])
+    R0 = Rg @ rot_from_rotvec(pert[3:])
+    t0 = tg + pert[:3]
+    Rrel = R0.T @ Rg
+    trel = R0.T @ (tg - t0)
+    return ScanProblem(np.ascontiguousarray(src), np.ascontiguousarray(target), R0, t0, init_particles(P, rng),
+                       np.r_[trel, rotvec_from_rot(Rrel)], Rg, tg)
+
+
 def make_uniform_problem(P: int, n_s: int, n_t: int, seed: int = 1, box: float = 20.0,
                          motion=(0.15, -0.08, 0.03, 0.0, 0.0, 0.01)) -> ScanProblem:
     """Small planted-motion problem (the survey's probe): target = random surface
