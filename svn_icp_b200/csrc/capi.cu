@@ -343,8 +343,11 @@ static int choose_shape(svnicp_handle h) {
   const int Kp = (h->K + 3) & ~3;
   h->Kp = Kp;
   int TB = 32;
-  const int S = 3;
-  while (TB > 4 && gn_stage_bytes(TB, Kp) * S > 100 * 1024) TB >>= 1;
+  int S = 3;
+  size_t budget = 100 * 1024;  // two CTAs of k_gn per SM (registers allow no more: measured)
+  if (const char *e = getenv("SVNICP_GN_STAGES")) S = atoi(e) > 1 ? atoi(e) : 2;          // tuning knobs (bench sweeps)
+  if (const char *e = getenv("SVNICP_GN_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
+  while (TB > 4 && gn_stage_bytes(TB, Kp) * S > budget) TB >>= 1;
   h->TB = TB;
   h->stages = S;
   h->gn_smem = gn_stage_bytes(TB, Kp) * S + 2 * S * sizeof(uint64_t) + 128;

@@ -282,7 +282,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 // UNI: every lane of a warp works on the same source point (PG >= 32) -> the early exit is a warp vote.
 template <bool DBG, bool UNI>
-__global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {
+__global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {  // (.., 3) spills the fp64 accumulators: measured slower
   if (a.ctrl->stop) return;
   extern __shared__ __align__(128) unsigned char smem[];
   const int TB = a.TB, Kp = a.Kp, S = a.stages;

@@ -1,0 +1,65 @@
+"""Worker for tests/test_gpu_multi.py: launched with torch.distributed.run, one rank per GPU.
+
+Runs one particle-sharded scan (one ncclAllGather per iteration) and compares it, on rank 0, with the same scan on a
+single GPU.  Exit code 0 = parity."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import svn_icp_b200 as sv
+    from svn_icp_b200 import synth
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for P, full, es in ((96, True, False), (37, False, False), (64, True, True)):
+        pb = synth.make_problem(P, sensor="32", scan_index=6, n_map_scans=6, seed=0xC0FFEE)
+        prm = sv.SteinICPParam(iterations=10, KNN_count=64, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
+                               convergence_threshold=2e-3)
+        icp = sv.SVNICP(prm, pb.init_pose, device=local)
+        uid = [sv.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        icp.init_sharding(uid[0], rank, world)
+        lo, hi = icp.slice()
+        assert hi - lo >= 1 and (hi - lo) <= -(-P // world)
+        icp.add_cloud(pb.source, pb.target, pb.init_pose)
+        icp.set_initial_mean(pb.R0, pb.t0)
+        assert icp.stein_align() == sv.ALIGN_SUCCESS
+        got = icp.get_particles()
+        mean, cov, its, hist = icp.get_transformation(), icp.get_cov_matrix(), icp.iterations_done(), icp.get_particle_history()
+        # every rank must hold the identical full result
+        t = torch.from_numpy(np.concatenate([got, mean, cov, [its]])).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        same = bool(torch.equal(t, ref))
+        if rank == 0:
+            single = sv.SVNICP(prm, pb.init_pose, device=local)
+            single.add_cloud(pb.source, pb.target, pb.init_pose)
+            single.set_initial_mean(pb.R0, pb.t0)
+            single.stein_align()
+            err = np.abs(single.get_particles() - got).max()
+            herr = np.abs(single.get_particle_history() - hist).max()
+            print(f"P={P} full={full} es={es} ranks={world}: |sharded - single| particles {err:.3e} history {herr:.3e} "
+                  f"iters {its} vs {single.iterations_done()}", flush=True)
+            # identical algorithm; only the grouping of the fp32 Gauss-Newton partial sums differs with the slice size
+            ok &= err < 1e-7 and herr < 1e-6 and its == single.iterations_done()
+        flag = torch.tensor([1 if (ok and same) else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+        icp.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
