@@ -1,0 +1,61 @@
+"""The header-only C++ mirror of the reference classes (svn_icp_b200/include/svnicp/SVNICP.hpp): compiles against the C ABI
+(CPU check) and, on a GPU, produces the same bits as the Python mirror."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import svn_icp_b200 as sv
+from svn_icp_b200 import synth
+from conftest import ROOT
+
+
+def build_mirror(tmp_path):
+    from svn_icp_b200 import build
+    lib = build.build()
+    exe = os.path.join(tmp_path, "mirror_main")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "svn_icp_b200", "include"),
+                           os.path.join(ROOT, "tests", "cpp", "mirror_main.cpp"), "-o", exe, lib,
+                           "-Wl,-rpath," + os.path.dirname(lib)])
+    return exe
+
+
+def test_mirror_compiles_and_links(tmp_path):
+    exe = build_mirror(str(tmp_path))
+    assert os.path.exists(exe)
+    # plain C consumers can include the ABI header too
+    c = os.path.join(tmp_path, "abi.c")
+    open(c, "w").write('#include "svnicp_b200.h"\nint main(void){svnicp_params p; svnicp_default_params(&p); return p.KNN_count==100?0:1;}\n')
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(tmp_path, "abi"),
+                           sv.LIB_PATH, "-Wl,-rpath," + os.path.dirname(sv.LIB_PATH)])
+    assert subprocess.call([os.path.join(tmp_path, "abi")]) == 0
+
+
+@pytest.mark.gpu
+def test_mirror_matches_python_mirror(tmp_path):
+    exe = build_mirror(str(tmp_path))
+    P, I, K = 48, 7, 40
+    pb = synth.make_uniform_problem(P, 900, 9000, seed=4)
+    prob, res = os.path.join(tmp_path, "problem.bin"), os.path.join(tmp_path, "result.bin")
+    with open(prob, "wb") as f:
+        f.write(struct.pack("6q", len(pb.source), len(pb.target), P, I, K, 1))
+        f.write(struct.pack("2d", 1.0, 3.0))
+        for a in (pb.source, pb.target, pb.init_pose, pb.R0, pb.t0):
+            f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    out = subprocess.run([exe, prob, res], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = np.fromfile(res, dtype=np.uint8)
+    d = np.frombuffer(raw[: 8 * (48 + 7 * P)].tobytes(), dtype=np.float64)
+    hist = np.frombuffer(raw[8 * (48 + 7 * P):].tobytes(), dtype=np.float32).reshape(I, 6 * P)
+    icp = sv.SVNICP(sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=3.0, lr=1.0, SVN_full_grad=True), pb.init_pose)
+    icp.add_cloud(pb.source, pb.target, pb.init_pose)
+    icp.set_initial_mean(pb.R0, pb.t0)
+    icp.stein_align()
+    np.testing.assert_array_equal(d[:6], icp.get_transformation())
+    np.testing.assert_array_equal(d[6:12], icp.get_distribution())
+    np.testing.assert_array_equal(d[12:48], icp.get_cov_matrix())
+    np.testing.assert_array_equal(d[48:48 + 6 * P], icp.get_particles())
+    np.testing.assert_array_equal(d[48 + 6 * P:], icp.get_particle_weight())
+    np.testing.assert_array_equal(hist, icp.get_particle_history())
