@@ -96,36 +96,46 @@ def make_problem(P, seed=0xC0FFEE):
     return pb, time.time() - t
 
 
-def cpu_baseline_port(pb, budget_s=20.0):
-    """The C restatement (OpenMP, all host cores) on a bounded sample: all particles, a subset of the source points
-    against the full map, 2 iterations; extrapolated linearly in N_s and iterations (the algorithm is linear in both)."""
+def _sampled_scan_time(run, ns_full, I, ns1, ns2):
+    """Affine model of the CPU scan time from four bounded runs: T(n_s, iters) = setup(n_s) + iters * (a + b n_s).
+    setup (the brute-force K-NN) and b (correspondence + Gauss-Newton) scale with N_s, a (the P x P Stein step) does not.
+    run(ns, iters) -> seconds.  Returns (t_scan_full, description)."""
+    T22, T21, T12, T11 = run(ns2, 2), run(ns2, 1), run(ns1, 2), run(ns1, 1)
+    it2, it1 = max(T22 - T21, 1e-9), max(T12 - T11, 1e-9)
+    b = max((it2 - it1) / (ns2 - ns1), 0.0)
+    a = max(it2 - b * ns2, 0.0)
+    setup2 = max(T21 - it2, 0.0)
+    t_scan = setup2 * ns_full / ns2 + I * (a + b * ns_full)
+    desc = (f"runs at N_s={ns1},{ns2} x iterations=1,2: setup {setup2:.2f}s@{ns2} pts, per iteration {a:.3f}s (Stein, N_s-independent) + "
+            f"{b * 1e3:.3f} ms/point; extrapolated to N_s={ns_full}, {I} iterations")
+    return t_scan, desc
+
+
+def _subsample(pb, ns, seed=1):
+    sel = np.sort(np.random.default_rng(seed).choice(len(pb.source), ns, replace=False))
+    return pb.source[sel]
+
+
+def cpu_baseline_port(pb):
+    """The C restatement (OpenMP, all host cores) on a bounded sample of the same workload (all particles, the full map,
+    subsets of the source points, 1-2 iterations), extrapolated with the affine model above."""
     import oracle as orc
     O = orc.Oracle()
-    cores = O.num_threads()
-    ns_full = len(pb.source)
-    ns = min(ns_full, 512)
-    rng = np.random.default_rng(1)
-    sel = np.sort(rng.choice(ns_full, ns, replace=False))
-    src = pb.source[sel]
     K, I = WORKLOAD["K"], WORKLOAD["iterations"]
-    t0 = time.time()
-    q0 = O.transform_q0(src, pb.R0, pb.t0)
-    cand, _ = O.knn_mink(q0, pb.target, K)
-    t_setup = time.time() - t0
-    prm = orc.make_params(iterations=2, knn_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], svn_full_grad=WORKLOAD["svn_full_grad"])
-    t0 = time.time()
-    O.align(prm, src, pb.target, pb.init_pose, pb.R0, pb.t0)
-    t_total = time.time() - t0
-    t_iter = max(t_total - t_setup, 1e-9) / 2
-    scale = ns_full / ns
-    t_scan = t_setup * scale + t_iter * scale * I
-    return dict(value=1.0 / t_scan, unit="scans/sec", cores=cores, kind="port",
-                sample=f"all {pb.init_pose.shape[1]} particles, {ns} of {ns_full} source points vs the full {len(pb.target)}-point map, "
-                       f"2 of {I} iterations; setup {t_setup:.2f}s + {t_iter:.2f}s/iter, scaled linearly in N_s and iterations")
+
+    def run(ns, iters):
+        prm = orc.make_params(iterations=iters, knn_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], svn_full_grad=WORKLOAD["svn_full_grad"])
+        t0 = time.time()
+        O.align(prm, _subsample(pb, ns), pb.target, pb.init_pose, pb.R0, pb.t0)
+        return time.time() - t0
+
+    t_scan, desc = _sampled_scan_time(run, len(pb.source), I, 256, 512)
+    return dict(value=1.0 / t_scan, unit="scans/sec", cores=O.num_threads(), kind="port",
+                sample=f"C port (OpenMP): all {pb.init_pose.shape[1]} particles, full {len(pb.target)}-point map; " + desc)
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own sources on the host cores (oracle/_ref), bounded sample per step."""
+    """--impl reference: the reference's own sources on the host cores (oracle/_ref; the C port if absent), bounded sample per step."""
     if rank != 0:
         return
     import oracle as orc
@@ -133,46 +143,32 @@ def run_reference(args, rank, world):
     pb, _ = make_problem(P)
     K, I = WORKLOAD["K"], WORKLOAD["iterations"]
     ns_full = len(pb.source)
-    ns = min(ns_full, 256)
-    sel = np.sort(np.random.default_rng(1).choice(ns_full, ns, replace=False))
-    src = pb.source[sel]
-    iters = 2
     if orc.ref_available():
-        ref = orc.Reference()
-        cores = ref.num_threads()
-        kind = "reference"
-        prm = orc.make_params(iterations=iters, knn_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], svn_full_grad=WORKLOAD["svn_full_grad"])
-
-        def step():
-            t0 = time.time()
-            out = ref.scan(prm, src, pb.target, pb.init_pose, pb.R0, pb.t0)
-            return time.time() - t0, out
+        eng = orc.Reference()
+        kind, cores = "reference", eng.num_threads()
+        call = lambda prm, src: eng.scan(prm, src, pb.target, pb.init_pose, pb.R0, pb.t0)
     else:
-        O = orc.Oracle()
-        cores = O.num_threads()
-        kind = "port"
-        prm = orc.make_params(iterations=iters, knn_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], svn_full_grad=WORKLOAD["svn_full_grad"])
+        eng = orc.Oracle()
+        kind, cores = "port", eng.num_threads()
+        call = lambda prm, src: eng.align(prm, src, pb.target, pb.init_pose, pb.R0, pb.t0)
 
-        def step():
-            t0 = time.time()
-            out = O.align(prm, src, pb.target, pb.init_pose, pb.R0, pb.t0)
-            return time.time() - t0, out
-    # one extra run with 1 iteration separates the per-scan setup from the per-iteration cost
-    prm1 = orc.make_params(iterations=1, knn_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], svn_full_grad=WORKLOAD["svn_full_grad"])
+    def run(ns, iters):
+        prm = orc.make_params(iterations=iters, knn_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], svn_full_grad=WORKLOAD["svn_full_grad"])
+        src = _subsample(pb, ns)
+        t0 = time.time()
+        call(prm, src)
+        return time.time() - t0
+
+    ns1, ns2 = 128, 256
     for _ in range(max(args.warmup, 1)):
-        step()
-    ts = [step()[0] for _ in range(args.steps)]
-    t2 = float(np.mean(ts))
-    t0 = time.time()
-    (ref.scan if kind == "reference" else O.align)(prm1, src, pb.target, pb.init_pose, pb.R0, pb.t0)
-    t1 = time.time() - t0
-    t_iter = max(t2 - t1, 1e-9) / (iters - 1)
-    t_setup = max(t1 - t_iter, 0.0)
-    scale = ns_full / ns
-    t_scan = scale * (t_setup + I * t_iter)
+        run(ns1, 1)
+    vals, desc = [], ""
+    for _ in range(args.steps):  # a step = one bounded sample (4 short runs) -> one extrapolated scan time
+        t_scan, desc = _sampled_scan_time(run, ns_full, I, ns1, ns2)
+        vals.append(t_scan)
+    t_scan = float(np.mean(vals))
     val = 1.0 / t_scan
-    sample = (f"{kind}: all {P} particles, {ns} of {ns_full} source points vs the full {len(pb.target)}-point map, {iters} of {I} iterations per step; "
-              f"setup {t_setup:.2f}s + {t_iter:.2f}s/iter, scaled linearly in N_s and iterations to the full scan")
+    sample = f"{kind} (libtorch CPU, device-swapped reference sources): all {P} particles, full {len(pb.target)}-point map; " + desc
     line = dict(metric=METRIC, value=val, unit="scans/sec", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=t_scan * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                 impl="reference", config=dict(workload="configs[1]: 64-beam synthetic scan, 1000 particles", n_s=ns_full, n_t=len(pb.target), **WORKLOAD),

@@ -13,7 +13,9 @@ LIB = os.path.join(LIBDIR, "libsvnicp_b200.so")
 SOURCES = ["cand_build.cu", "iter_kernels.cu", "stein_kernels.cu", "capi.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "svnicp_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+# extra -D switches for A/B builds (e.g. SVNICP_NVCC_DEFS="-DSVN_GN_ACC2_FP32 -DSVN_GN_MINBLOCKS=3")
+EXTRA = os.environ.get("SVNICP_NVCC_DEFS", "").split()
+FLAGS = EXTRA + ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "-ccbin", "/usr/bin/g++", "-I", "/usr/include"]
 
 

@@ -47,6 +47,7 @@ struct Ctrl {
   // median radix select (lower median of P^2 pairwise squared distances, SVNICP.cpp:262)
   unsigned long long sel_prefix[MED_PASSES + 1];
   unsigned long long sel_rank[MED_PASSES + 1];
+  unsigned med_ticket[MED_PASSES];  // CTAs that finished pass s (the last one selects)
   unsigned long long kept_total;  // sum of ccount over rows (prune statistics)
 };
 

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
       base += __popc(m);
     }
     // pad to a multiple of 4 with sentinels that can never win (d = inf, strict '<') so k_gn scans in chunks of 4
-    const int padded = (base + 3) & ~3;
+    const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);  // k_gn scans 2, then chunks of 4
     if (lane < padded - base) out[base + lane] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
     if (lane == 0) { a.ccount[b] = padded; kept += (unsigned long long)base; }
   }
@@ -268,6 +268,18 @@ __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
 constexpr int GN_CONSUMERS = 256;
 constexpr int GN_THREADS = GN_CONSUMERS + 32;
 constexpr int GN_FLUSH_ROWS = 32;
+// Three-level accumulation of the 16 Gauss-Newton sums: fp32 over GN_FLUSH_ROWS rows -> accum2_t registers over
+// GN_FLUSH2 such flushes -> the thread's fp64 partial slot.  fp32 second level: measured 30.3 vs 35.5 ms per scan at
+// configs[1] against an fp64 second level (-DSVN_GN_ACC2_FP64), at <= ~5e-7 relative error in H and b.
+constexpr int GN_FLUSH2 = 64;
+#ifdef SVN_GN_ACC2_FP64
+typedef double accum2_t;
+#else
+typedef float accum2_t;
+#endif
+#ifndef SVN_GN_MINBLOCKS
+#define SVN_GN_MINBLOCKS 2
+#endif
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
@@ -282,7 +294,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 // UNI: every lane of a warp works on the same source point (PG >= 32) -> the early exit is a warp vote.
 template <bool DBG, bool UNI>
-__global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {  // (.., 3) spills the fp64 accumulators: measured slower
+__global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a) {  // (.., 3) spills the fp64 accumulators: measured slower
   if (a.ctrl->stop) return;
   extern __shared__ __align__(128) unsigned char smem[];
   const int TB = a.TB, Kp = a.Kp, S = a.stages;
@@ -337,10 +349,12 @@ __global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {  // (.., 3) 
   }
   const float Dm = a.max_dist;
   float acc[NACC];
-  double dacc[NACC];
+  accum2_t dacc[NACC];  // second-level accumulators (see SVN_GN_ACC2_FP32)
 #pragma unroll
-  for (int i = 0; i < NACC; i++) { acc[i] = 0.f; dacc[i] = 0.0; }
-  int rows_in_acc = 0;
+  for (int i = 0; i < NACC; i++) { acc[i] = 0.f; dacc[i] = 0; }
+  int rows_in_acc = 0, flushes2 = 0;
+  bool wrote = false;
+  double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + (active ? l : 0)) * NACC;
   const int row_step = RG * Kp;
 
 // one candidate: fixed operation order (index parity with oracle_corr_f32); strict '<', first slot wins (mink.cuh:141)
@@ -367,7 +381,8 @@ __global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {  // (.., 3) 
         float4 sv_nx = sv;
         if (r + RG < TB) { n_nx = cnt[r + RG]; sv_nx = src[r + RG]; }
         if (n != 0) {
-          float4 c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
+          float4 c0 = e[0], c1 = e[1], c2, c3;
+          if (n > 2) { c2 = e[2]; c3 = e[3]; }
           // a = A' s' ; q = a + tau : query relative to q0_b.  Order fixed (index parity).
           const float ax = __fmaf_rn(A0, sv.x, __fmaf_rn(A1, sv.y, __fmul_rn(A2, sv.z)));
           const float ay = __fmaf_rn(A3, sv.x, __fmaf_rn(A4, sv.y, __fmul_rn(A5, sv.z)));
@@ -375,7 +390,8 @@ __global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {  // (.., 3) 
           const float qx = __fadd_rn(ax, t0), qy = __fadd_rn(ay, t1), qz = __fadd_rn(az, t2);
           float best = INFINITY;
           int bi = 0;
-          SVN_EVAL(c0, 0) SVN_EVAL(c1, 1) SVN_EVAL(c2, 2) SVN_EVAL(c3, 3)
+          SVN_EVAL(c0, 0) SVN_EVAL(c1, 1)
+          if (n > 2) { SVN_EVAL(c2, 2) SVN_EVAL(c3, 3) }
           if (n > 4) {
             // upper bound of |q| (distance of this particle's query from the initial-guess query q0_b)
             const float qn = fmaf(sqrt_approx(fmaf(qz, qz, fmaf(qy, qy, qx * qx))), 1.00001f, 1e-7f);
@@ -430,8 +446,16 @@ __global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {  // (.., 3) 
       }
       if (rows_in_acc >= GN_FLUSH_ROWS) {
 #pragma unroll
-        for (int j = 0; j < NACC; j++) { dacc[j] += (double)acc[j]; acc[j] = 0.f; }
+        for (int j = 0; j < NACC; j++) { dacc[j] += (accum2_t)acc[j]; acc[j] = 0.f; }
         rows_in_acc = 0;
+        if (++flushes2 >= GN_FLUSH2 && active) {
+          // third level: fold into this thread's own fp64 partial slot (global, L2-resident) so that the fp32
+          // second level never carries more than GN_FLUSH2 * GN_FLUSH_ROWS rows, whatever the slice length
+#pragma unroll
+          for (int j = 0; j < NACC; j++) { out[j] = (wrote ? out[j] : 0.0) + (double)dacc[j]; dacc[j] = 0; }
+          wrote = true;
+          flushes2 = 0;
+        }
       }
     }
     __syncwarp();
@@ -439,9 +463,8 @@ __global__ void __launch_bounds__(GN_THREADS, 2) k_gn(IterArgs a) {  // (.., 3) 
   }
 #undef SVN_EVAL
   if (active) {
-    double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + l) * NACC;
 #pragma unroll
-    for (int j = 0; j < NACC; j++) out[j] = dacc[j] + (double)acc[j];
+    for (int j = 0; j < NACC; j++) out[j] = (wrote ? out[j] : 0.0) + ((double)dacc[j] + (double)acc[j]);
   }
 }
 

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(1024) k_decide(SteinArgs a, int epilogue) {
     a.xs[i] = a.rec[(size_t)p * REC + REC_X + comp];
   }
   for (int i = tid; i < MED_PASSES * MED_BINS; i += blockDim.x) a.hist[i] = 0u;
+  if (tid < MED_PASSES) c->med_ticket[tid] = 0u;
   if (tid == 0) {
     c->sel_prefix[0] = 0ull;
     c->sel_rank[0] = ((unsigned long long)a.P * (unsigned long long)a.P - 1ull) / 2ull;  // lower median
@@ -97,7 +98,7 @@ __device__ void select_from_hist(const unsigned *hist, unsigned long long prefix
   unsigned long long loc = 0;
   for (int i = 0; i < per; i++) {
     const int b = tid * per + i;
-    if (b < nbins) loc += hist[b];
+    if (b < nbins) loc += __ldcg(hist + b);  // written by other CTAs' atomics: read at L2
   }
   unsigned long long incl = loc;
 #pragma unroll
@@ -115,7 +116,7 @@ __device__ void select_from_hist(const unsigned *hist, unsigned long long prefix
     unsigned long long cum = excl;
     int b = tid * per;
     for (;; b++) {
-      const unsigned long long h = hist[b];
+      const unsigned long long h = __ldcg(hist + b);
       if (cum + h > rank_in) break;
       cum += h;
     }
@@ -138,18 +139,18 @@ __device__ __forceinline__ double pair_d2(const double *__restrict__ xs, int P, 
   return s;
 }
 
-// one radix-select pass over the upper triangle of D (D_ij = D_ji counted twice, diagonal once)
-__global__ void __launch_bounds__(256) k_median_pass(SteinArgs a, int s) {
+// one radix-select pass over the upper triangle of D (D_ij = D_ji counted twice, diagonal once).  Few fat CTAs; the LAST
+// CTA to finish (ticket counter) turns the histogram into the next (prefix, rank) -- and after the final pass into the
+// bandwidth h = median / log(P + 1) (SVNICP.cpp:262, Q4) -- so no other kernel has to rescan histograms.
+constexpr int MED_THREADS = 512;
+
+__global__ void __launch_bounds__(MED_THREADS) k_median_pass(SteinArgs a, int s) {
   Ctrl *c = a.ctrl;
   if (c->stop) return;
   __shared__ unsigned s_hist[MED_BINS];
+  __shared__ int s_last;
   const int tid = threadIdx.x;
-  unsigned long long prefix = c->sel_prefix[0], rank = c->sel_rank[0];
-  if (s > 0) {
-    select_from_hist(a.hist + (size_t)(s - 1) * MED_BINS, c->sel_prefix[s - 1], c->sel_rank[s - 1], 1 << pass_bits(s - 1),
-                     pass_bits(s - 1), &prefix, &rank);
-    if (blockIdx.x == 0 && tid == 0) { c->sel_prefix[s] = prefix; c->sel_rank[s] = rank; }
-  }
+  const unsigned long long prefix = c->sel_prefix[s];
   const int nb = 1 << pass_bits(s);
   for (int i = tid; i < nb; i += blockDim.x) s_hist[i] = 0u;
   __syncthreads();
@@ -168,35 +169,41 @@ __global__ void __launch_bounds__(256) k_median_pass(SteinArgs a, int s) {
   unsigned *gh = a.hist + (size_t)s * MED_BINS;
   for (int i = tid; i < nb; i += blockDim.x)
     if (s_hist[i]) atomicAdd(&gh[i], s_hist[i]);
-}
-
-// bandwidth from the finished select: h = median / log(P + 1)   (SVNICP.cpp:262, Q4)
-__device__ double finish_bandwidth(const SteinArgs &a) {
-  const Ctrl *c = a.ctrl;
-  unsigned long long prefix, rank;
-  const int s = MED_PASSES;
-  select_from_hist(a.hist + (size_t)(s - 1) * MED_BINS, c->sel_prefix[s - 1], c->sel_rank[s - 1], 1 << pass_bits(s - 1),
-                   pass_bits(s - 1), &prefix, &rank);
-  const double med = __longlong_as_double((long long)prefix);
-  return med / log((double)(a.P + 1));
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&c->med_ticket[s], 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  unsigned long long np, nr;
+  select_from_hist(gh, prefix, c->sel_rank[s], nb, pass_bits(s), &np, &nr);
+  if (tid == 0) {
+    c->sel_prefix[s + 1] = np;
+    c->sel_rank[s + 1] = nr;
+    if (s == MED_PASSES - 1) c->bandwidth = __longlong_as_double((long long)np) / log((double)(a.P + 1));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_stein_full: SVNICP::svn_full_grad (SVNICP.cpp:229-252).  8 warps = 8 particles i per CTA; the
-// records of 32 particles j are staged in shared memory per step; lane = j.
+// k_stein_full: SVNICP::svn_full_grad (SVNICP.cpp:229-252).  A CTA owns ST_NI particles i; each is served by ST_JQ warps
+// that split every 128-wide j tile of the 33-double record (staged in shared memory) into quarters; lane = j.
+// Fixed summation order (lane-strided per quarter, xor tree, quarters 0..3), identical on every rank.
 // ---------------------------------------------------------------------------------------------
 constexpr int ST_WARPS = 8;
 constexpr int ST_TJ = 32;    // j-tile of the pre-conditioned SVGD kernel
-constexpr int ST_TJF = 128;  // j-tile of the full SVN kernel (4 j per lane per tile)
+constexpr int ST_TJF = 128;  // j-tile of the full SVN kernel
+constexpr int ST_JQ = 4;     // warps per particle
+constexpr int ST_NI = ST_WARPS / ST_JQ;
 
 __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_full(SteinArgs a) {
   Ctrl *c = a.ctrl;
   if (c->stop) return;
   __shared__ double s_rec[33][ST_TJF + 1];
-  const double h = finish_bandwidth(a);
-  if (blockIdx.x == 0 && threadIdx.x == 0) c->bandwidth = h;
+  __shared__ double s_part[ST_WARPS][28];
+  const double h = c->bandwidth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int l = blockIdx.x * ST_WARPS + warp;
+  const int ii = warp / ST_JQ, jq = warp % ST_JQ;
+  const int l = blockIdx.x * ST_NI + ii;
   const bool active = l < a.P_l;
   const int i = a.p_lo + (active ? l : 0);
   double xi[6];
@@ -215,41 +222,50 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_full(SteinArgs a) {
       s_rec[q][jj] = (j0 + jj < a.P) ? a.rec[(size_t)(j0 + jj) * REC + q] : 0.0;
     }
     __syncthreads();
-    if (active) {
-      // lane handles j = j0 + lane, +32, +64, +96 (fixed order: the N-GPU run sums in the same order)
-#pragma unroll 2
-      for (int u = 0; u < ST_TJF / 32; u++) {
-        const int jj = u * 32 + lane;
-        if (j0 + jj >= a.P) break;
-        double dl[6], D = 0.0;
+    const int jj = jq * 32 + lane;
+    if (active && j0 + jj < a.P) {
+      double dl[6], D = 0.0;
 #pragma unroll
-        for (int d = 0; d < 6; d++) { dl[d] = xi[d] - s_rec[REC_X + d][jj]; D += dl[d] * dl[d]; }
-        const double kij = exp(-D / h);          // :264
-        const double k2 = kij * kij;             // :238
-        double g[6];
+      for (int d = 0; d < 6; d++) { dl[d] = xi[d] - s_rec[REC_X + d][jj]; D += dl[d] * dl[d]; }
+      const double kij = exp(-D / h);          // :264
+      const double k2 = kij * kij;             // :238
+      double g[6];
 #pragma unroll
-        for (int d = 0; d < 6; d++) g[d] = two_over_h * (dl[d] * kij);  // :233
-        int q = 0;
+      for (int d = 0; d < 6; d++) g[d] = two_over_h * (dl[d] * kij);  // :233
+      int q = 0;
 #pragma unroll
-        for (int r = 0; r < 6; r++)
+      for (int r = 0; r < 6; r++)
 #pragma unroll
-          for (int cc = r; cc < 6; cc++, q++) Hm[q] += k2 * s_rec[REC_H + q][jj] + g[r] * g[cc];  // :236-242
+        for (int cc = r; cc < 6; cc++, q++) Hm[q] += k2 * s_rec[REC_H + q][jj] + g[r] * g[cc];  // :236-242
 #pragma unroll
-        for (int d = 0; d < 6; d++) v[d] += g[d] - kij * s_rec[REC_B + d][jj];  // :244 with b' = -b
-      }
+      for (int d = 0; d < 6; d++) v[d] += g[d] - kij * s_rec[REC_B + d][jj];  // :244 with b' = -b
     }
   }
 #pragma unroll
   for (int q = 0; q < 21; q++) Hm[q] = warp_sum(Hm[q]);
 #pragma unroll
   for (int q = 0; q < 6; q++) v[q] = warp_sum(v[q]);
-  if (active && lane == 0) {
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 21; q++) s_part[warp][q] = Hm[q];
+#pragma unroll
+    for (int q = 0; q < 6; q++) s_part[warp][21 + q] = v[q];
+  }
+  __syncthreads();
+  if (active && jq == 0 && lane == 0) {
     double A[36], x[6];
-    const double invP = 1.0 / (double)a.P;
     for (int r = 0; r < 6; r++)
-      for (int cc = r; cc < 6; cc++) { A[6 * r + cc] = Hm[tri(r, cc)] / (double)a.P; A[6 * cc + r] = A[6 * r + cc]; }
-    for (int d = 0; d < 6; d++) x[d] = v[d] / (double)a.P;
-    (void)invP;
+      for (int cc = r; cc < 6; cc++) {
+        double sum = 0.0;
+        for (int w = 0; w < ST_JQ; w++) sum += s_part[ii * ST_JQ + w][tri(r, cc)];
+        A[6 * r + cc] = sum / (double)a.P;
+        A[6 * cc + r] = A[6 * r + cc];
+      }
+    for (int d = 0; d < 6; d++) {
+      double sum = 0.0;
+      for (int w = 0; w < ST_JQ; w++) sum += s_part[ii * ST_JQ + w][21 + d];
+      x[d] = sum / (double)a.P;
+    }
     lu_solve6(A, x, 1);  // :250 (the reference forms the explicit inverse; tolerance-level difference)
     for (int d = 0; d < 6; d++) a.delta[(size_t)l * 6 + d] = a.lr * x[d];
   }
@@ -293,8 +309,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_svgd(SteinArgs a) {
   Ctrl *c = a.ctrl;
   if (c->stop) return;
   __shared__ double s_rec[12][ST_TJ + 1];
-  const double h = finish_bandwidth(a);
-  if (blockIdx.x == 0 && threadIdx.x == 0) c->bandwidth = h;
+  const double h = c->bandwidth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int l = blockIdx.x * ST_WARPS + warp;
   const bool active = l < a.P_l;
@@ -451,8 +466,8 @@ int launch_decide(const SteinArgs &a, cudaStream_t st, int epilogue) {
 
 int launch_median(const SteinArgs &a, cudaStream_t st) {
   if (a.P < 2) return 0;
-  int grid = a.P < a.sm_count * 4 ? a.P : a.sm_count * 4;
-  for (int s = 0; s < MED_PASSES; s++) k_median_pass<<<grid, 256, 0, st>>>(a, s);
+  const int grid = a.P < a.sm_count ? a.P : a.sm_count;
+  for (int s = 0; s < MED_PASSES; s++) k_median_pass<<<grid, MED_THREADS, 0, st>>>(a, s);
   return MED_PASSES;
 }
 
@@ -463,7 +478,7 @@ int launch_stein(const SteinArgs &a, cudaStream_t st) {
   }
   const int grid = cdiv(a.P_l, ST_WARPS);
   if (a.svn_full_grad) {
-    k_stein_full<<<grid, ST_WARPS * 32, 0, st>>>(a);
+    k_stein_full<<<cdiv(a.P_l, ST_NI), ST_WARPS * 32, 0, st>>>(a);
     return 1;
   }
   k_mean_hessian<<<1, 1024, 0, st>>>(a);
