@@ -89,7 +89,8 @@ struct svnicp_handle_t {
   ScanConst sc;
   // device buffers
   DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, rec, xs, delta, Hbar_inv, stats, particles, init_pose;
-  DevBuf<float4> sp, cand, clist;
+  DevBuf<float4> sp, cand, clist, spair;
+  int pair_mode = 0;
   DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc, cand_idx;
   int Kp = 100;  // misc: [0] cursor, [1] fallback count
   DevBuf<unsigned long long> keys, kept_hist;
@@ -200,7 +201,7 @@ static int alloc_particle_state(svnicp_handle h) {
   CU(h->t.ensure(3 * P, true));
   CU(h->dnorm.ensure(P, true));
   CU(h->rec.ensure(P * REC, true));
-  CU(h->xs.ensure(6 * P));
+  CU(h->xs.ensure(39 * P));  // SoA copy of the gathered record (RT_ROWS x P)
   CU(h->delta.ensure(6 * P, true));
   CU(h->Hbar_inv.ensure(36));
   CU(h->stats.ensure(48));
@@ -250,6 +251,7 @@ int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_
     h->stream = h->own_stream;
     for (int i = 0; i < 4; i++) CU(cudaEventCreate(&h->ev[i]));
     init_iter_kernels();
+    init_pair_kernels();
     CU(cudaGetLastError());
     int r = alloc_particle_state(h);
     if (r) return r;
@@ -278,7 +280,7 @@ void svnicp_destroy(svnicp_handle h) {
   DevBuf<double> *d[] = {&h->src64, &h->tgt64, &h->q0, &h->sxyz, &h->R, &h->t, &h->dnorm, &h->part, &h->rec, &h->xs, &h->delta,
                          &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose};
   for (auto *b : d) b->release();
-  h->sp.release(); h->cand.release(); h->clist.release();
+  h->sp.release(); h->cand.release(); h->clist.release(); h->spair.release();
   h->cand_idx.release();
   h->ccount.release(); h->counts.release(); h->starts.release(); h->fill.release(); h->pt_slot.release(); h->sidx.release(); h->misc.release();
   h->keys.release(); h->kept_hist.release(); h->xf.release(); h->history.release(); h->hist.release(); h->ctrl.release();
@@ -347,14 +349,21 @@ static int choose_shape(svnicp_handle h) {
   size_t budget = 100 * 1024;  // two CTAs of k_gn per SM (registers allow no more: measured)
   if (const char *e = getenv("SVNICP_GN_STAGES")) S = atoi(e) > 1 ? atoi(e) : 2;          // tuning knobs (bench sweeps)
   if (const char *e = getenv("SVNICP_GN_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
-  while (TB > 4 && gn_stage_bytes(TB, Kp) * S > budget) TB >>= 1;
+  // Default: the scalar kernel (256 consumers, two CTAs per SM).  SVNICP_GN_PAIR=1 selects the packed-fp32x2 pair mode
+  // (gn_pair.cu, 512 threads, one CTA per SM; needs >= 32 local particles so a warp shares a source point).  Measured at
+  // configs[1]: pair mode issues 33 % fewer instructions but is not faster (32.7 vs 30.6 ms of k_gn per scan) because
+  // FFMA2 delivers the same 32 results/clk/SMSP as scalar FFMA (scripts/micro/ffma2_bench.cu) -- see DESIGN.md.
+  h->pair_mode = (h->P_l >= 32 && getenv("SVNICP_GN_PAIR")) ? 1 : 0;
+  const int consumers = h->pair_mode ? 512 : 256;
+  if (h->pair_mode && !getenv("SVNICP_GN_SMEM_KB")) budget = 160 * 1024;
+  while (TB > (h->pair_mode ? 8 : 4) && gn_stage_bytes(TB, Kp) * S > budget) TB >>= 1;
   h->TB = TB;
   h->stages = S;
   h->gn_smem = gn_stage_bytes(TB, Kp) * S + 2 * S * sizeof(uint64_t) + 128;
   int PG = 1;
-  while (PG < h->P_l && PG < 256) PG <<= 1;
+  while (PG < h->P_l && PG < consumers) PG <<= 1;
   h->PG = PG;
-  h->RG = 256 / PG;
+  h->RG = consumers / PG;
   h->n_pgroups = (h->P_l + PG - 1) / PG;
   if (h->n_pgroups < 1) h->n_pgroups = 1;
   return SVNICP_OK;
@@ -378,6 +387,7 @@ int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int sou
   h->n_pad = n_pad;
   CU(h->q0.ensure((size_t)3 * n_s));
   CU(h->sp.ensure((size_t)n_pad + 64));
+  CU(h->spair.ensure((size_t)n_pad + 64));
   CU(h->cand.ensure((size_t)n_s * h->K));
   CU(h->cand_idx.ensure((size_t)n_s * h->K));
   CU(h->clist.ensure((size_t)n_pad * h->Kp));
@@ -393,7 +403,7 @@ int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int sou
   CU(h->sidx.ensure((size_t)n_t));
   CU(h->sxyz.ensure((size_t)3 * n_t));
   const int n_tiles = n_pad / TB;
-  int n_slices = (2 * h->sm_count) / h->n_pgroups;
+  int n_slices = ((h->pair_mode ? 1 : 2) * h->sm_count) / h->n_pgroups;
   if (n_slices < 1) n_slices = 1;
   if (n_slices > n_tiles) n_slices = n_tiles;
   h->n_slices = n_slices;
@@ -482,6 +492,7 @@ int svnicp_align(svnicp_handle h) {
   cb.sxyz = h->sxyz.p; cb.sidx = h->sidx.p; cb.cand = h->cand.p; cb.cand_idx = h->cand_idx.p;
   cb.sm_count = h->sm_count;
   h->launches += launch_cand_build(cb, st);
+  if (h->pair_mode) h->launches += launch_spair(h->sp.p, h->spair.p, h->n_pad, st);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev[1], st));
 
@@ -492,6 +503,7 @@ int svnicp_align(svnicp_handle h) {
   ia.sc = h->sc;
   ia.max_dist = (float)h->max_dist;
   ia.sp = h->sp.p; ia.cand = h->cand.p; ia.clist = h->clist.p; ia.ccount = h->ccount.p;
+  ia.spair = h->spair.p; ia.pair_mode = h->pair_mode;
   ia.R = h->R.p; ia.t = h->t.p; ia.xf = h->xf.p; ia.dnorm = h->dnorm.p; ia.part = h->part.p; ia.rec = h->rec.p; ia.ctrl = h->ctrl.p;
   ia.TB = h->TB; ia.stages = h->stages; ia.n_slices = h->n_slices; ia.n_pgroups = h->n_pgroups; ia.PG = h->PG; ia.RG = h->RG;
   ia.gn_smem = h->gn_smem; ia.sm_count = h->sm_count; ia.svn_full_grad = h->prm.SVN_full_grad;
@@ -527,9 +539,9 @@ int svnicp_align(svnicp_handle h) {
     PROF(0);
     h->launches += launch_prep(ia, st, 0);
     PROF(1);
-    h->launches += launch_filter(ia, st);
+    h->launches += h->pair_mode ? launch_filter_pair(ia, st) : launch_filter(ia, st);
     PROF(2);
-    h->launches += launch_gn(ia, st);
+    h->launches += h->pair_mode ? launch_gn_pair(ia, st) : launch_gn(ia, st);
     PROF(3);
     h->launches += launch_finalize(ia, st);
     PROF(4);

@@ -39,6 +39,8 @@ struct IterArgs {
   float max_dist;
   // buffers
   const float4 *sp, *cand;
+  const float4 *spair;  // [n_pad/2][2] interleaved source pairs (pair mode)
+  int pair_mode;        // 1: clist/ccount hold the interleaved pair lists of gn_pair.cu
   float4 *clist;
   int *ccount;
   double *R, *t;       // [P][9], [P][3]
@@ -57,6 +59,11 @@ struct IterArgs {
   uint8_t *dbg_mask;
 };
 int launch_prep(const IterArgs &a, cudaStream_t st, int x_only);
+// packed fp32x2 "pair mode" (gn_pair.cu): two source points per thread step
+void init_pair_kernels();
+int launch_spair(const float4 *sp, float4 *spair, int n_pad, cudaStream_t st);
+int launch_filter_pair(const IterArgs &a, cudaStream_t st);
+int launch_gn_pair(const IterArgs &a, cudaStream_t st);
 int launch_filter(const IterArgs &a, cudaStream_t st);
 int launch_gn(const IterArgs &a, cudaStream_t st);
 int launch_finalize(const IterArgs &a, cudaStream_t st);

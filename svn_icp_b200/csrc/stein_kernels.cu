@@ -38,10 +38,15 @@ __global__ void k_particles_init(double *R, double *t, const double *init_pose, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_decide: early-stop decision for the PREVIOUS iteration + its history row; resets the median select.
-// One CTA.  Runs after the all-gather, so every rank takes the same decision from the same record.
+// k_decide: early-stop decision for the PREVIOUS iteration + its history row; builds the SoA copy of the gathered
+// record the Stein kernels read; resets the median select.  Runs after the all-gather, so every rank (and every CTA:
+// the decision is recomputed redundantly from the same record) decides identically.
+// recT rows: 0..32 = rec[0..32] (x, b, H), 33..38 = rec[34..39] (g).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_decide(SteinArgs a, int epilogue) {
+constexpr int RT_ROWS = 39;
+constexpr int DECIDE_THREADS = 512;
+
+__global__ void __launch_bounds__(DECIDE_THREADS) k_decide(SteinArgs a, int epilogue) {
   Ctrl *c = a.ctrl;
   if (c->stop) return;
   __shared__ double s_part[32];
@@ -60,27 +65,30 @@ __global__ void __launch_bounds__(1024) k_decide(SteinArgs a, int epilogue) {
     int stop = 0;
     if (a.check_early_stop && it > 0 && tot / (double)a.P < a.threshold) stop = 1;
     s_stop = stop;
-    if (stop) { c->stop = 1; c->iters_done = it; }
-    else if (epilogue) c->iters_done = it;
+    if (blockIdx.x == 0) {
+      if (stop) { c->stop = 1; c->iters_done = it; }
+      else if (epilogue) c->iters_done = it;
+    }
   }
   __syncthreads();
   if (s_stop) return;  // break BEFORE the history row of that iteration (Q9)
+  const int gtid = blockIdx.x * blockDim.x + tid, gn = gridDim.x * blockDim.x;
   if (it > 0) {
     float *row = a.history + (size_t)(it - 1) * 6 * a.P;
-    for (int i = tid; i < 6 * a.P; i += blockDim.x) {
+    for (int i = gtid; i < 6 * a.P; i += gn) {
       const int comp = i / a.P, p = i % a.P;
       row[i] = (float)a.rec[(size_t)p * REC + REC_X + comp];
     }
   }
   if (epilogue) return;
-  if (tid == 0 && a.kept_hist) a.kept_hist[it] = c->kept_total;
-  for (int i = tid; i < 6 * a.P; i += blockDim.x) {
-    const int comp = i / a.P, p = i % a.P;
-    a.xs[i] = a.rec[(size_t)p * REC + REC_X + comp];
+  for (int i = gtid; i < RT_ROWS * a.P; i += gn) {
+    const int row = i / a.P, p = i % a.P;
+    a.xs[i] = a.rec[(size_t)p * REC + (row < 33 ? row : row + 1)];
   }
-  for (int i = tid; i < MED_PASSES * MED_BINS; i += blockDim.x) a.hist[i] = 0u;
-  if (tid < MED_PASSES) c->med_ticket[tid] = 0u;
-  if (tid == 0) {
+  for (int i = gtid; i < MED_PASSES * MED_BINS; i += gn) a.hist[i] = 0u;
+  if (gtid < MED_PASSES) c->med_ticket[gtid] = 0u;
+  if (gtid == 0) {
+    if (a.kept_hist) a.kept_hist[it] = c->kept_total;
     c->sel_prefix[0] = 0ull;
     c->sel_rank[0] = ((unsigned long long)a.P * (unsigned long long)a.P - 1ull) / 2ull;  // lower median
   }
@@ -217,9 +225,21 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_full(SteinArgs a) {
   const double two_over_h = 2.0 / h;
   for (int j0 = 0; j0 < a.P; j0 += ST_TJF) {
     __syncthreads();
-    for (int e = tid; e < 33 * ST_TJF; e += blockDim.x) {
-      const int jj = e / 33, q = e % 33;
-      s_rec[q][jj] = (j0 + jj < a.P) ? a.rec[(size_t)(j0 + jj) * REC + q] : 0.0;
+    {
+      // coalesced rows of the SoA record copy; all loads are issued before the first store (one L2 round trip per tile)
+      constexpr int NLD = (33 * ST_TJF + ST_WARPS * 32 - 1) / (ST_WARPS * 32);
+      double tmp[NLD];
+#pragma unroll
+      for (int u = 0; u < NLD; u++) {
+        const int e = tid + u * ST_WARPS * 32;
+        const int q = e / ST_TJF, jj = e % ST_TJF;
+        tmp[u] = (e < 33 * ST_TJF && j0 + jj < a.P) ? __ldg(a.xs + (size_t)q * a.P + j0 + jj) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < NLD; u++) {
+        const int e = tid + u * ST_WARPS * 32;
+        if (e < 33 * ST_TJF) s_rec[e / ST_TJF][e % ST_TJF] = tmp[u];
+      }
     }
     __syncthreads();
     const int jj = jq * 32 + lane;
@@ -323,9 +343,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_svgd(SteinArgs a) {
   for (int j0 = 0; j0 < a.P; j0 += ST_TJ) {
     __syncthreads();
     for (int e = tid; e < 12 * ST_TJ; e += blockDim.x) {
-      const int jj = e / 12, q = e % 12;
-      const int col = (q < 6) ? (REC_X + q) : (REC_G + q - 6);
-      s_rec[q][jj] = (j0 + jj < a.P) ? a.rec[(size_t)(j0 + jj) * REC + col] : 0.0;
+      const int q = e / ST_TJ, jj = e % ST_TJ;
+      const int row = (q < 6) ? q : (33 + q - 6);  // x rows 0..5, g rows 33..38 of the SoA record copy
+      s_rec[q][jj] = (j0 + jj < a.P) ? a.xs[(size_t)row * a.P + j0 + jj] : 0.0;
     }
     __syncthreads();
     if (active && j0 + lane < a.P) {
@@ -460,7 +480,7 @@ int launch_init_particles(double *R, double *t, const double *init_pose_dev, int
 }
 
 int launch_decide(const SteinArgs &a, cudaStream_t st, int epilogue) {
-  k_decide<<<1, 1024, 0, st>>>(a, epilogue);
+  k_decide<<<epilogue ? 4 : 32, DECIDE_THREADS, 0, st>>>(a, epilogue);
   return 1;
 }
 

@@ -254,3 +254,30 @@ def test_errors(small):
         icp.stein_align()
     with pytest.raises(sv.SvnIcpError, match="empty cloud"):
         icp.add_cloud(np.zeros((0, 3)), small.target, np.zeros((6, 4)))
+
+
+@pytest.mark.parametrize("odd", [False, True])
+def test_pair_mode_same_bits(oracle, lidar, monkeypatch, odd):
+    """SVNICP_GN_PAIR=1 (packed fp32x2 kernels, two source points per thread step) must choose exactly the same
+    correspondences and produce the same poses as the default scalar kernels; odd N_s exercises the half-empty last pair."""
+    src = lidar.source[:-1] if odd else lidar.source
+    res = {}
+    for mode in ("scalar", "pair"):
+        if mode == "pair":
+            monkeypatch.setenv("SVNICP_GN_PAIR", "1")
+        else:
+            monkeypatch.delenv("SVNICP_GN_PAIR", raising=False)
+        icp = sv.SVNICP(sv.SteinICPParam(iterations=1, KNN_count=100, max_dist=3.0, lr=1.0, debug_corr=True), lidar.init_pose)
+        icp.add_cloud(src, lidar.target, lidar.init_pose)
+        icp.set_initial_mean(lidar.R0, lidar.t0)
+        icp.stein_align()
+        xf, idx, mask = icp.get_correspondences()
+        H, b, _ = icp.get_gn_system()
+        res[mode] = (xf, idx, mask, H, b, icp.get_particles())
+    for k in range(3):
+        np.testing.assert_array_equal(res["pair"][k], res["scalar"][k])
+    np.testing.assert_allclose(res["pair"][3], res["scalar"][3], rtol=2e-6)
+    np.testing.assert_allclose(res["pair"][5], res["scalar"][5], rtol=0, atol=1e-7)
+    cidx, rel = icp.get_candidates(want_rel=True)
+    oidx, omask = oracle.corr_f32(res["pair"][0], icp.get_source_f32(), rel, cidx, 3.0)
+    np.testing.assert_array_equal(res["pair"][1], oidx)
