@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--particles", type=int, default=WORKLOAD["particles"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -294,6 +295,48 @@ def main():
                                      ms_per_launch=t_filter * 1e3),
                     fp32=dict(achieved_tflops=f_alg / t_pass / 1e12, peak_tflops=fp32_peak, frac=f_alg / t_pass / 1e12 / fp32_peak,
                               note="brute-force-equivalent flops P*N_s*(130+8K); exact pruning skips most of them"))
+    # dram__bytes_{read,write}.sum per launch from the committed ncu --set full captures (profiles/), if present
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        roofline["traffic"] = tr["k_filter_bytes_per_launch"] + tr["k_gn_bytes_per_launch_late"]
+        roofline["traffic_detail"] = tr
+    except Exception:
+        pass
+
+    # secondary variants of the same scan: the reference's own pre-processing (uniform down-sampling
+    # 0.5 m then 1.5 m voxels, OdometryPipeline.cpp:559-560) and reference-style early stop (geodeAlpha.yaml:9,17-19)
+    variants = {}
+    if world == 1 and not args.no_variants:
+        ds = synth.uniform_downsample(synth.uniform_downsample(pb.source, 0.5), 1.5)
+        ds_dev = torch.from_numpy(np.ascontiguousarray(ds)).to(dev)
+
+        def scan_ds(i):
+            icp.add_cloud_device(ds_dev.data_ptr(), len(ds), tgt_dev.data_ptr(), n_t, particles[i])
+            icp.set_initial_mean(pb.R0, pb.t0)
+            icp.stein_align()
+            return icp.get_transformation()
+
+        scan_ds(0)
+        ms_ds, mean_ds = timed(scan_ds, 1, args.steps)
+        variants["downsampled_source"] = dict(n_s=int(len(ds)), scans_per_sec=args.steps / (ms_ds * 1e-3), ms_per_scan=ms_ds / args.steps,
+                                              mean=[float(v) for v in mean_ds])
+        prm_es = sv.SteinICPParam(iterations=100, KNN_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"],
+                                  SVN_full_grad=WORKLOAD["svn_full_grad"], check_early_stop=True, convergence_threshold=5e-4)
+        icp_es = sv.SVNICP(prm_es, particles[0], device=local_rank)
+        icp_es.set_stream(stream.cuda_stream)
+
+        def scan_es(i):
+            icp_es.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, particles[i])
+            icp_es.set_initial_mean(pb.R0, pb.t0)
+            icp_es.stein_align()
+            return icp_es.get_transformation()
+
+        scan_es(0)
+        ms_es, _ = timed(scan_es, 1, args.steps)
+        variants["early_stop_thr5e-4_max100"] = dict(scans_per_sec=args.steps / (ms_es * 1e-3), ms_per_scan=ms_es / args.steps,
+                                                     iterations_executed=icp_es.iterations_done())
+        icp_es.close()
+
     if rank == 0:
         h2d = (n_s + n_t) * 24 + 6 * P * 8
         d2h = (48 + 6 * P) * 8
@@ -305,7 +348,7 @@ def main():
                                 particles_per_gpu=P_g, **WORKLOAD),
                     e2e=dict(value=args.steps / (ms_e2e * 1e-3), unit="scans/sec", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=int(launches), roofline=roofline, clocks=clocks,
-                    phases_ms_per_scan=ph, scan_info=info, prune_mean_kept=[round(float(x), 2) for x in prune],
+                    phases_ms_per_scan=ph, scan_info=info, prune_mean_kept=[round(float(x), 2) for x in prune], variants=variants,
                     check=dict(mean=[float(v) for v in out[0]], gt=[float(v) for v in pb.gt_rel]), datagen_s=gen_s)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(pb)
