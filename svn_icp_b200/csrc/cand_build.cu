@@ -148,7 +148,7 @@ __device__ __forceinline__ double dist2(const double q[3], const double *__restr
 }
 
 __global__ void __launch_bounds__(KNN_WARPS * 32)
-k_knn(const double *__restrict__ q0, int n_s, const double *__restrict__ tgt, int n_t, const double *__restrict__ sxyz,
+k_knn(const double *__restrict__ q0, int row_lo, int row_hi, const double *__restrict__ tgt, int n_t, const double *__restrict__ sxyz,
       const int *__restrict__ sidx, const unsigned long long *__restrict__ keys, const int *__restrict__ starts,
       const int *__restrict__ counts, unsigned mask, double cell, int K, float4 *__restrict__ cand, int *__restrict__ cand_idx,
       int *__restrict__ fallback_count) {
@@ -159,7 +159,7 @@ k_knn(const double *__restrict__ q0, int n_s, const double *__restrict__ tgt, in
   const double inv_cell = 1.0 / cell;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (int b = blockIdx.x * KNN_WARPS + warp; b < n_s; b += gridDim.x * KNN_WARPS) {
+  for (int b = row_lo + blockIdx.x * KNN_WARPS + warp; b < row_hi; b += gridDim.x * KNN_WARPS) {
     const double q[3] = {q0[3 * b], q0[3 * b + 1], q0[3 * b + 2]};
     const int c0[3] = {cell_of(q[0], inv_cell), cell_of(q[1], inv_cell), cell_of(q[2], inv_cell)};
     int count = 0;
@@ -333,10 +333,11 @@ int launch_cand_build(const CandBuildArgs &a, cudaStream_t st) {
     cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes());
     attr_set = true;
   }
-  int grid = cdiv(a.n_s, KNN_WARPS);
+  int grid = cdiv(a.row_hi - a.row_lo, KNN_WARPS);
   const int max_grid = a.sm_count * 12;
   if (grid > max_grid) grid = max_grid;
-  k_knn<<<grid, KNN_WARPS * 32, knn_smem_bytes(), st>>>(a.q0, a.n_s, a.tgt64, a.n_t, a.sxyz, a.sidx, a.keys, a.starts, a.counts,
+  if (grid < 1) grid = 1;
+  k_knn<<<grid, KNN_WARPS * 32, knn_smem_bytes(), st>>>(a.q0, a.row_lo, a.row_hi, a.tgt64, a.n_t, a.sxyz, a.sidx, a.keys, a.starts, a.counts,
                                                          (unsigned)(a.table_size - 1), a.cell, a.K, a.cand, a.cand_idx, a.fallback_count);
   launches++;
   return launches;

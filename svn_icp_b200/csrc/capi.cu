@@ -91,6 +91,7 @@ struct svnicp_handle_t {
   DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, rec, xs, delta, Hbar_inv, stats, particles, init_pose;
   DevBuf<float4> sp, cand, clist, spair;
   int pair_mode = 0;
+  int rows_per_rank = 0;
   DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc, cand_idx;
   int Kp = 100;  // misc: [0] cursor, [1] fallback count
   DevBuf<unsigned long long> keys, kept_hist;
@@ -388,8 +389,10 @@ int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int sou
   CU(h->q0.ensure((size_t)3 * n_s));
   CU(h->sp.ensure((size_t)n_pad + 64));
   CU(h->spair.ensure((size_t)n_pad + 64));
-  CU(h->cand.ensure((size_t)n_s * h->K));
-  CU(h->cand_idx.ensure((size_t)n_s * h->K));
+  // candidate rows are built sharded across the ranks and all-gathered once per scan: n_ranks blocks of rows_per_rank rows
+  h->rows_per_rank = (int)((n_s + h->n_ranks - 1) / h->n_ranks);
+  CU(h->cand.ensure((size_t)h->rows_per_rank * h->n_ranks * h->K));
+  CU(h->cand_idx.ensure((size_t)h->rows_per_rank * h->n_ranks * h->K));
   CU(h->clist.ensure((size_t)n_pad * h->Kp));
   CU(h->ccount.ensure((size_t)n_pad + 64));
   CU(cudaMemsetAsync(h->ccount.p, 0, ((size_t)n_pad + 64) * sizeof(int), h->stream));
@@ -491,7 +494,17 @@ int svnicp_align(svnicp_handle h) {
   cb.table_size = (int)table;
   cb.sxyz = h->sxyz.p; cb.sidx = h->sidx.p; cb.cand = h->cand.p; cb.cand_idx = h->cand_idx.p;
   cb.sm_count = h->sm_count;
+  cb.row_lo = h->rank * h->rows_per_rank;
+  cb.row_hi = cb.row_lo + h->rows_per_rank < (int)h->n_s ? cb.row_lo + h->rows_per_rank : (int)h->n_s;
+  if (cb.row_hi < cb.row_lo) cb.row_hi = cb.row_lo;
   h->launches += launch_cand_build(cb, st);
+  if (h->n_ranks > 1) {
+    // per-scan exchange: every rank built the K-NN rows of its block only (exact and deterministic, so the gathered
+    // table equals the single-GPU table bit for bit); in place, this rank's block already sits at its offset
+    const size_t blk = (size_t)h->rows_per_rank * h->K;
+    NC(g_nccl.AllGather(h->cand.p + (size_t)h->rank * blk, h->cand.p, blk * 4, ncclFloat, h->comm, st));
+    NC(g_nccl.AllGather(h->cand_idx.p + (size_t)h->rank * blk, h->cand_idx.p, blk, ncclInt32, h->comm, st));
+  }
   if (h->pair_mode) h->launches += launch_spair(h->sp.p, h->spair.p, h->n_pad, st);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev[1], st));

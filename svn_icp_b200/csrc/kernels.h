@@ -9,6 +9,7 @@ namespace svn {
 struct CandBuildArgs {
   const double *src64, *tgt64;
   int n_s, n_pad, n_t, K;
+  int row_lo, row_hi;  // source rows whose candidates THIS rank builds (sharded across ranks, then all-gathered)
   ScanConst sc;
   double cell;
   double *q0;     // [n_s][3]
