@@ -149,6 +149,8 @@ int svnicp_set_profiling(svnicp_handle h, int on);
 int svnicp_get_phase_times(svnicp_handle h, double out8[8]);
 /* {n_s, n_t, K, brute-force fallback queries of the candidate builder, TB, n_slices, n_pgroups, iterations enqueued} */
 int svnicp_get_scan_info(svnicp_handle h, int64_t out8[8]);
+/* globaltimer stamps (ns) of the phase boundaries inside the last fused Stein-phase kernel (CTA 0): tuning aid */
+int svnicp_get_tail_stamps(svnicp_handle h, double out10[10]);
 /* number of kernel launches issued by the last svnicp_align */
 int svnicp_get_launch_count(svnicp_handle h, int64_t *out);
 

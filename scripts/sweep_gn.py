@@ -11,3 +11,5 @@ for _ in range(3):
     icp.add_cloud(pb.source, pb.target, pb.init_pose); icp.set_initial_mean(pb.R0, pb.t0); icp.stein_align()
 ph = icp.get_phase_times(); t = icp.get_timing(); info = icp.get_scan_info()
 print(os.environ.get("SVNICP_GN_STAGES"), os.environ.get("SVNICP_GN_SMEM_KB"), "TB", info["TB"], "gn_ms %.2f stein_ms %.2f setup %.2f total %.2f" % (ph["gn_ms"], ph["stein_ms"], ph["setup_ms"], t["total_ms"]))
+ts = icp.get_tail_stamps()
+print("tail phases us: decide %.1f | sync %.1f | median %.1f | stein %.1f | sync %.1f | update %.1f | sync %.1f | radius %.1f | sync %.1f  total %.1f" % tuple(list(np.diff(ts) / 1e3) + [(ts[-1] - ts[0]) / 1e3]))

@@ -73,7 +73,7 @@ EXPORTS = [
     "svnicp_initialize_particles", "svnicp_initialize_particles_gaussian", "svnicp_iterations_done", "svnicp_get_candidates",
     "svnicp_get_source_f32", "svnicp_get_correspondences", "svnicp_get_gn_system", "svnicp_get_stein", "svnicp_get_prune_stats",
     "svnicp_get_timing", "svnicp_get_slice", "svnicp_get_launch_count", "svnicp_set_profiling", "svnicp_get_phase_times",
-    "svnicp_get_scan_info",
+    "svnicp_get_scan_info", "svnicp_get_tail_stamps",
 ]
 
 
@@ -332,6 +332,11 @@ class SVNICP:
         self._check(self._lib.svnicp_get_scan_info(self._h, _p(out)), "get_scan_info")
         names = ["n_s", "n_t", "K", "knn_fallback_queries", "TB", "n_slices", "n_pgroups", "iterations_enqueued"]
         return dict(zip(names, out.tolist()))
+
+    def get_tail_stamps(self):
+        out = np.zeros(10)
+        self._check(self._lib.svnicp_get_tail_stamps(self._h, _p(out)), "get_tail_stamps")
+        return out
 
     def launch_count(self) -> int:
         v = C.c_int64(0)

@@ -88,14 +88,15 @@ struct svnicp_handle_t {
   bool have_cloud = false, aligned = false;
   ScanConst sc;
   // device buffers
-  DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, rec, xs, delta, Hbar_inv, stats, particles, init_pose;
+  DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, rec, xs, delta, Hbar_inv, stats, particles, init_pose, prep_scratch_d;
+  DevBuf<int> prep_scratch_i;
   DevBuf<float4> sp, cand, clist, spair;
   int pair_mode = 0;
   int rows_per_rank = 0;
   DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc, cand_idx;
   int Kp = 100;  // misc: [0] cursor, [1] fallback count
   DevBuf<unsigned long long> keys, kept_hist;
-  DevBuf<float> xf, history;
+  DevBuf<float> xf, history, dbg_xf;
   DevBuf<unsigned> hist;
   DevBuf<Ctrl> ctrl;
   DevBuf<int32_t> dbg_idx;
@@ -209,6 +210,8 @@ static int alloc_particle_state(svnicp_handle h) {
   CU(h->particles.ensure(6 * P));
   CU(h->xf.ensure(12 * P));
   CU(h->hist.ensure((size_t)MED_PASSES * MED_BINS));
+  CU(h->prep_scratch_d.ensure((size_t)h->sm_count * 12 + 64, true));
+  CU(h->prep_scratch_i.ensure(PRUNE_BINS + 8, true));
   CU(h->ctrl.ensure(1, true));
   CU(h->misc.ensure(8, true));
   const size_t I = (size_t)(h->prm.iterations > 0 ? h->prm.iterations : 1);
@@ -279,12 +282,13 @@ void svnicp_destroy(svnicp_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   DevBuf<double> *d[] = {&h->src64, &h->tgt64, &h->q0, &h->sxyz, &h->R, &h->t, &h->dnorm, &h->part, &h->rec, &h->xs, &h->delta,
-                         &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose};
+                         &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose, &h->prep_scratch_d};
+  h->prep_scratch_i.release();
   for (auto *b : d) b->release();
   h->sp.release(); h->cand.release(); h->clist.release(); h->spair.release();
   h->cand_idx.release();
   h->ccount.release(); h->counts.release(); h->starts.release(); h->fill.release(); h->pt_slot.release(); h->sidx.release(); h->misc.release();
-  h->keys.release(); h->kept_hist.release(); h->xf.release(); h->history.release(); h->hist.release(); h->ctrl.release();
+  h->keys.release(); h->kept_hist.release(); h->xf.release(); h->dbg_xf.release(); h->history.release(); h->hist.release(); h->ctrl.release();
   h->dbg_idx.release(); h->dbg_mask.release();
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->h_particles) cudaFreeHost(h->h_particles);
@@ -532,6 +536,11 @@ int svnicp_align(svnicp_handle h) {
   sa.Hbar_inv = h->Hbar_inv.p; sa.hist = h->hist.p; sa.history = h->history.p; sa.ctrl = h->ctrl.p;
   sa.stats = h->stats.p; sa.particles = h->particles.p; sa.sm_count = h->sm_count;
   sa.kept_hist = h->kept_hist.p;
+  sa.prep_scratch_d = h->prep_scratch_d.p;
+  sa.prep_scratch_i = h->prep_scratch_i.p;
+  // one cooperative kernel per iteration for decide + median + Stein + update + next prep (tail_fused.cu);
+  // SVNICP_NO_FUSED_TAIL=1 keeps the nine separate launches (A/B measurements, same-bits test)
+  const bool fused_tail = getenv("SVNICP_NO_FUSED_TAIL") == nullptr;
 
   if (h->profile)
     while (h->prof_events.size() < (size_t)I * 7) {
@@ -550,21 +559,31 @@ int svnicp_align(svnicp_handle h) {
     }
 #define PROF(k) do { if (h->profile) CU(cudaEventRecord(h->prof_events[(size_t)e * 7 + (k)], st)); } while (0)
     PROF(0);
-    h->launches += launch_prep(ia, st, 0);
+    if (!fused_tail || e == 0) h->launches += launch_prep(ia, st, 0);  // the fused tail prepares the next iteration itself
     PROF(1);
     h->launches += h->pair_mode ? launch_filter_pair(ia, st) : launch_filter(ia, st);
     PROF(2);
     h->launches += h->pair_mode ? launch_gn_pair(ia, st) : launch_gn(ia, st);
+    if (h->prm.debug_corr) {  // parity tap: the transforms this iteration's correspondences were computed with
+      CU(h->dbg_xf.ensure((size_t)(h->P_l > 0 ? h->P_l : 1) * 12));
+      CU(cudaMemcpyAsync(h->dbg_xf.p, h->xf.p, (size_t)h->P_l * 12 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
     PROF(3);
     h->launches += launch_finalize(ia, st);
     PROF(4);
     int rc = do_allgather(h);
     if (rc) return rc;
     PROF(5);
-    h->launches += launch_decide(sa, st, 0);
-    h->launches += launch_median(sa, st);
-    h->launches += launch_stein(sa, st);
-    h->launches += launch_update(sa, st);
+    if (fused_tail) {
+      const int n = launch_tail_fused(sa, ia, st);
+      if (n < 0) return fail(h, SVNICP_ERR_CUDA, "cooperative launch of k_tail_fused failed: %s", cudaGetErrorString(cudaGetLastError()));
+      h->launches += n;
+    } else {
+      h->launches += launch_decide(sa, st, 0);
+      h->launches += launch_median(sa, st);
+      h->launches += launch_stein(sa, st);
+      h->launches += launch_update(sa, st);
+    }
     PROF(6);
 #undef PROF
     CU(cudaGetLastError());
@@ -728,7 +747,7 @@ int svnicp_get_correspondences(svnicp_handle h, float *out_xf, int32_t *out_idx,
   if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
   if (!h->prm.debug_corr) return fail(h, SVNICP_ERR_INVALID, "created without debug_corr");
   CU(cudaSetDevice(h->device));
-  if (out_xf) CU(cudaMemcpy(out_xf, h->xf.p, (size_t)h->P_l * 12 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out_xf) CU(cudaMemcpy(out_xf, h->dbg_xf.p, (size_t)h->P_l * 12 * sizeof(float), cudaMemcpyDeviceToHost));
   if (out_idx) CU(cudaMemcpy(out_idx, h->dbg_idx.p, (size_t)h->P_l * h->n_s * sizeof(int32_t), cudaMemcpyDeviceToHost));
   if (out_mask) CU(cudaMemcpy(out_mask, h->dbg_mask.p, (size_t)h->P_l * h->n_s, cudaMemcpyDeviceToHost));
   return SVNICP_OK;
@@ -800,6 +819,13 @@ int svnicp_get_scan_info(svnicp_handle h, int64_t out8[8]) {
   if (!h || !out8) return SVNICP_ERR_INVALID;
   out8[0] = h->n_s; out8[1] = h->n_t; out8[2] = h->K; out8[3] = h->fallback_queries;
   out8[4] = h->TB; out8[5] = h->n_slices; out8[6] = h->n_pgroups; out8[7] = h->enqueued_iters;
+  return SVNICP_OK;
+}
+
+int svnicp_get_tail_stamps(svnicp_handle h, double out10[10]) {
+  if (!h || !out10) return SVNICP_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpy(out10, h->prep_scratch_d.p + (size_t)h->sm_count * 12, 10 * sizeof(double), cudaMemcpyDeviceToHost));
   return SVNICP_OK;
 }
 

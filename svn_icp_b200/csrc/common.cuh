@@ -134,4 +134,27 @@ __device__ inline void so3_log(const double R[9], double w[3]) {
   }
 }
 
+// largest eigenvalue of M^T M (M 3x3 row-major) = sigma_max(M)^2, rounded up; NaN propagates
+__device__ inline double sym3_max_eig_MtM(const double M[9]) {
+  double B[6];  // 00 01 02 11 12 22
+  B[0] = M[0] * M[0] + M[3] * M[3] + M[6] * M[6];
+  B[1] = M[0] * M[1] + M[3] * M[4] + M[6] * M[7];
+  B[2] = M[0] * M[2] + M[3] * M[5] + M[6] * M[8];
+  B[3] = M[1] * M[1] + M[4] * M[4] + M[7] * M[7];
+  B[4] = M[1] * M[2] + M[4] * M[5] + M[7] * M[8];
+  B[5] = M[2] * M[2] + M[5] * M[5] + M[8] * M[8];
+  const double tr = B[0] + B[3] + B[5];
+  const double q = tr / 3.0;
+  const double p1 = B[1] * B[1] + B[2] * B[2] + B[4] * B[4];
+  const double p2 = (B[0] - q) * (B[0] - q) + (B[3] - q) * (B[3] - q) + (B[5] - q) * (B[5] - q) + 2.0 * p1;
+  const double p = sqrt(p2 / 6.0);
+  if (!(p > 1e-300)) return (tr != tr) ? tr : q * (1.0 + 1e-9);
+  const double c00 = (B[0] - q) / p, c11 = (B[3] - q) / p, c22 = (B[5] - q) / p, c01 = B[1] / p, c02 = B[2] / p, c12 = B[4] / p;
+  double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+  r = fmin(fmax(r, -1.0), 1.0);
+  const double lam = q + 2.0 * p * cos(acos(r) / 3.0);
+  // never above the Frobenius bound (= trace), never optimistic: 1e-9 relative + absolute guard for rounding
+  return fmin(tr, lam * (1.0 + 1e-9) + 1e-30) * (tr == tr ? 1.0 : NAN);
+}
+
 }  // namespace svn

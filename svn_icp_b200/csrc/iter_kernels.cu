@@ -57,29 +57,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// largest eigenvalue of M^T M (M 3x3 row-major) = sigma_max(M)^2, rounded up; NaN propagates
-__device__ inline double sym3_max_eig_MtM(const double M[9]) {
-  double B[6];  // 00 01 02 11 12 22
-  B[0] = M[0] * M[0] + M[3] * M[3] + M[6] * M[6];
-  B[1] = M[0] * M[1] + M[3] * M[4] + M[6] * M[7];
-  B[2] = M[0] * M[2] + M[3] * M[5] + M[6] * M[8];
-  B[3] = M[1] * M[1] + M[4] * M[4] + M[7] * M[7];
-  B[4] = M[1] * M[2] + M[4] * M[5] + M[7] * M[8];
-  B[5] = M[2] * M[2] + M[5] * M[5] + M[8] * M[8];
-  const double tr = B[0] + B[3] + B[5];
-  const double q = tr / 3.0;
-  const double p1 = B[1] * B[1] + B[2] * B[2] + B[4] * B[4];
-  const double p2 = (B[0] - q) * (B[0] - q) + (B[3] - q) * (B[3] - q) + (B[5] - q) * (B[5] - q) + 2.0 * p1;
-  const double p = sqrt(p2 / 6.0);
-  if (!(p > 1e-300)) return (tr != tr) ? tr : q * (1.0 + 1e-9);
-  const double c00 = (B[0] - q) / p, c11 = (B[3] - q) / p, c22 = (B[5] - q) / p, c01 = B[1] / p, c02 = B[2] / p, c12 = B[4] / p;
-  double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
-  r = fmin(fmax(r, -1.0), 1.0);
-  const double lam = q + 2.0 * p * cos(acos(r) / 3.0);
-  // never above the Frobenius bound (= trace), never optimistic: 1e-9 relative + absolute guard for rounding
-  return fmin(tr, lam * (1.0 + 1e-9) + 1e-30) * (tr == tr ? 1.0 : NAN);
-}
-
 // ---------------------------------------------------------------------------------------------
 // k_prep
 // ---------------------------------------------------------------------------------------------
@@ -477,9 +454,19 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a) {
   const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (l >= a.P_l) return;
   const int nrows = a.n_slices * a.RG;
-  double s = 0.0;
-  if (lane < NACC)
-    for (int r = 0; r < nrows; r++) s += a.part[((size_t)r * a.P_l + l) * NACC + lane];  // fixed order
+  // fixed order: lane j (+16) sums the even (odd) partial rows of sum j with 4 independent chains, then odd joins even
+  const int j16 = lane & 15, half = lane >> 4;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int r = half;
+  for (; r + 6 < nrows; r += 8) {
+    s0 += a.part[((size_t)r * a.P_l + l) * NACC + j16];
+    s1 += a.part[((size_t)(r + 2) * a.P_l + l) * NACC + j16];
+    s2 += a.part[((size_t)(r + 4) * a.P_l + l) * NACC + j16];
+    s3 += a.part[((size_t)(r + 6) * a.P_l + l) * NACC + j16];
+  }
+  for (; r < nrows; r += 2) s0 += a.part[((size_t)r * a.P_l + l) * NACC + j16];
+  double s = (s0 + s1) + (s2 + s3);
+  s += __shfl_down_sync(0xffffffffu, s, 16);
   double v[NACC];
 #pragma unroll
   for (int j = 0; j < NACC; j++) v[j] = __shfl_sync(0xffffffffu, s, j);

@@ -88,8 +88,12 @@ struct SteinArgs {
   double *stats;     // [6 + 6 + 36] mean, var, cov
   double *particles; // [6][P]
   unsigned long long *kept_hist;  // [I] candidates kept by the prune pass per iteration (statistics)
+  double *prep_scratch_d;         // [sm_count][12] per-CTA partial sums of the fused tail kernel
+  int *prep_scratch_i;            // [PRUNE_BINS + 3] envelope / alpha / beta / NaN flag maxima (bit patterns)
   int sm_count;
 };
+// the whole Stein phase of one iteration as ONE cooperative kernel (tail_fused.cu); returns launches or -1
+int launch_tail_fused(const SteinArgs &a, const IterArgs &ia, cudaStream_t st);
 int launch_decide(const SteinArgs &a, cudaStream_t st, int epilogue);
 int launch_median(const SteinArgs &a, cudaStream_t st);
 int launch_stein(const SteinArgs &a, cudaStream_t st);

@@ -103,10 +103,13 @@ __device__ void select_from_hist(const unsigned *hist, unsigned long long prefix
   __shared__ unsigned long long s_res[2];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int per = (nbins + nt - 1) / nt;
+  unsigned vals[16];  // per <= 16 (8192 bins / 512 threads): all loads in flight at once, kept in registers
   unsigned long long loc = 0;
-  for (int i = 0; i < per; i++) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
     const int b = tid * per + i;
-    if (b < nbins) loc += __ldcg(hist + b);  // written by other CTAs' atomics: read at L2
+    vals[i] = (i < per && b < nbins) ? __ldcg(hist + b) : 0u;  // written by other CTAs' atomics: read at L2
+    loc += vals[i];
   }
   unsigned long long incl = loc;
 #pragma unroll
@@ -122,12 +125,14 @@ __device__ void select_from_hist(const unsigned *hist, unsigned long long prefix
   const unsigned long long excl = wbase + incl - loc;
   if (loc > 0 && excl <= rank_in && rank_in < excl + loc) {  // exactly one thread owns the rank
     unsigned long long cum = excl;
-    int b = tid * per;
-    for (;; b++) {
-      const unsigned long long h = __ldcg(hist + b);
-      if (cum + h > rank_in) break;
-      cum += h;
+    int b = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      if (cum + vals[i] > rank_in) break;
+      cum += vals[i];
+      b = i + 1;
     }
+    b += tid * per;
     s_res[0] = (prefix_in << bits) | (unsigned long long)b;
     s_res[1] = rank_in - cum;
   }

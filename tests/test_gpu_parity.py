@@ -256,6 +256,31 @@ def test_errors(small):
         icp.add_cloud(np.zeros((0, 3)), small.target, np.zeros((6, 4)))
 
 
+@pytest.mark.parametrize("P,full,es", [(64, True, False), (64, False, False), (1, True, False), (200, True, True), (9, False, True)])
+def test_fused_tail_same_bits(lidar, monkeypatch, P, full, es):
+    """The cooperative one-kernel Stein phase (tail_fused.cu, default) against the nine separate kernels
+    (SVNICP_NO_FUSED_TAIL=1): same arithmetic and summation orders -> identical particles, history and stop iteration."""
+    rng = np.random.default_rng(P)
+    init = synth.init_particles(P, rng)
+    res = {}
+    for mode in ("separate", "fused"):
+        if mode == "separate":
+            monkeypatch.setenv("SVNICP_NO_FUSED_TAIL", "1")
+        else:
+            monkeypatch.delenv("SVNICP_NO_FUSED_TAIL", raising=False)
+        icp = sv.SVNICP(sv.SteinICPParam(iterations=14, KNN_count=50, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
+                                         convergence_threshold=3e-3), init)
+        icp.add_cloud(lidar.source[::3], lidar.target, init)
+        icp.set_initial_mean(lidar.R0, lidar.t0)
+        icp.stein_align()
+        res[mode] = (icp.get_particles(), icp.get_particle_history(), icp.iterations_done(), icp.get_cov_matrix(), icp.launch_count())
+    np.testing.assert_array_equal(res["fused"][0], res["separate"][0])
+    np.testing.assert_array_equal(res["fused"][1], res["separate"][1])
+    assert res["fused"][2] == res["separate"][2]
+    np.testing.assert_array_equal(res["fused"][3], res["separate"][3])
+    assert res["fused"][4] < res["separate"][4]
+
+
 @pytest.mark.parametrize("odd", [False, True])
 def test_pair_mode_same_bits(oracle, lidar, monkeypatch, odd):
     """SVNICP_GN_PAIR=1 (packed fp32x2 kernels, two source points per thread step) must choose exactly the same
