@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(MED_THREADS) k_median_pass(SteinArgs a, int s)
 constexpr int ST_WARPS = 8;
 constexpr int ST_TJ = 32;    // j-tile of the pre-conditioned SVGD kernel
 constexpr int ST_TJF = 128;  // j-tile of the full SVN kernel
-constexpr int ST_JQ = 4;     // warps per particle
+constexpr int ST_JQ = 2;     // warps per particle
 constexpr int ST_NI = ST_WARPS / ST_JQ;
 
 __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_full(SteinArgs a) {
@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_full(SteinArgs a) {
       }
     }
     __syncthreads();
-    const int jj = jq * 32 + lane;
+    for (int u = 0; u < ST_TJF / 32 / ST_JQ; u++) {  // this warp's share of the tile, ascending j (fixed order)
+    const int jj = (jq * (ST_TJF / 32 / ST_JQ) + u) * 32 + lane;
     if (active && j0 + jj < a.P) {
       double dl[6], D = 0.0;
 #pragma unroll
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stein_full(SteinArgs a) {
         for (int cc = r; cc < 6; cc++, q++) Hm[q] += k2 * s_rec[REC_H + q][jj] + g[r] * g[cc];  // :236-242
 #pragma unroll
       for (int d = 0; d < 6; d++) v[d] += g[d] - kij * s_rec[REC_B + d][jj];  // :244 with b' = -b
+    }
     }
   }
 #pragma unroll

@@ -23,7 +23,7 @@ namespace svn {
 constexpr int TF_THREADS = 512;
 constexpr int TF_WARPS = TF_THREADS / 32;
 constexpr int TF_TJ = 128;  // j tile of the full SVN step
-constexpr int TF_JQ = 4;    // warps per particle (same split as k_stein_full)
+constexpr int TF_JQ = 2;    // warps per particle (same split as k_stein_full): 8 particles per CTA pass
 constexpr int TF_NI = TF_WARPS / TF_JQ;
 constexpr int TF_RT_ROWS = 39;
 
@@ -78,10 +78,11 @@ __device__ __forceinline__ unsigned long long tf_now() { unsigned long long t; a
 // phase time stamps of CTA 0 (ns), written behind the per-CTA partial sums: [sm_count*12 + k]
 #define TF_STAMP(k) do { if (gtid == 0) a.prep_scratch_d[(size_t)gridDim.x * 12 + (k)] = (double)tf_now(); } while (0)
 
-__global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterArgs ia) {
+__global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterArgs ia, int xs_smem_bytes) {
   cg::grid_group grid = cg::this_grid();
   Ctrl *c = a.ctrl;
   if (c->stop) return;  // set by an earlier launch: identical for every CTA
+  extern __shared__ __align__(16) unsigned char s_dyn[];  // optional copy of x [6][P] for the median passes
   __shared__ __align__(16) unsigned char s_raw[33 * (TF_TJ + 1) * 8];  // histogram (32 KB) / record tile (34 KB), never live together
   __shared__ double s_part[TF_WARPS][28];
   __shared__ double s_red[32][21];
@@ -137,6 +138,14 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
   // ------------------------------------------------------------------ bandwidth: exact lower median, 5 radix passes
   double h = 0.0;
   if (P > 1) {
+    // the 5 passes re-read x for every pair: keep it in shared memory when it fits (no L2 round trip per row)
+    const double *X = a.xs;
+    if (xs_smem_bytes > 0) {
+      double *sx = reinterpret_cast<double *>(s_dyn);
+      for (int i = tid; i < 6 * P; i += blockDim.x) sx[i] = __ldcg(a.xs + i);
+      __syncthreads();
+      X = sx;
+    }
     unsigned long long prefix = 0ull, rank = ((unsigned long long)P * (unsigned long long)P - 1ull) / 2ull;
     for (int s = 0; s < MED_PASSES; s++) {
       const int nb = 1 << tf_pass_bits(s);
@@ -145,18 +154,32 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
       const int consumed = tf_bits_before(s);
       const int shift = 63 - consumed - tf_pass_bits(s);
       const unsigned bmask = (unsigned)(nb - 1);
+      // upper triangle, each D_ij = D_ji counted twice; lanes that fall into the same bin are aggregated with
+      // match.any before the shared-memory atomic (the first pass puts nearly every pair into 2-3 exponent bins)
       for (int i = blockIdx.x; i < P; i += gridDim.x)
-        for (int j = i + tid; j < P; j += blockDim.x) {
-          double d2 = 0.0;
+        for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
+          const int j = j0 + tid;
+          bool match = false;
+          unsigned bin = 0;
+          if (j < P) {
+            double d2 = 0.0;
 #pragma unroll
-          for (int d = 0; d < 6; d++) {
-            const double df = a.xs[d * P + i] - a.xs[d * P + j];
-            d2 += df * df;  // SVNICP.cpp:257-260
+            for (int d = 0; d < 6; d++) {
+              const double df = X[d * P + i] - X[d * P + j];
+              d2 += df * df;  // SVNICP.cpp:257-260
+            }
+            const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
+            match = (consumed == 0) || ((key >> (63 - consumed)) == prefix);
+            bin = (unsigned)(key >> shift) & bmask;
           }
-          const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
-          const bool match = (consumed == 0) || ((key >> (63 - consumed)) == prefix);
-          if (match) atomicAdd(&s_hist[(unsigned)(key >> shift) & bmask], (j == i) ? 1u : 2u);
+          const unsigned mm = __ballot_sync(0xffffffffu, match);
+          if (match) {
+            const unsigned peers = __match_any_sync(mm, bin);
+            if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));
+          }
         }
+      // the P diagonal entries are exact zeros (key 0): they match only an all-zero prefix and fall into bin 0
+      if (blockIdx.x == 0 && tid == 0 && (consumed == 0 || prefix == 0ull)) atomicAdd(&s_hist[0], (unsigned)P);
       __syncthreads();
       unsigned *gh = a.hist + (size_t)s * MED_BINS;
       for (int i = tid; i < nb; i += blockDim.x)
@@ -214,7 +237,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
           }
         }
         __syncthreads();
-        const int jj = jq * 32 + lane;
+        for (int u = 0; u < TF_TJ / 32 / TF_JQ; u++) {  // this warp's share of the tile, ascending j (fixed order)
+        const int jj = (jq * (TF_TJ / 32 / TF_JQ) + u) * 32 + lane;
         if (active && j0 + jj < P) {
           double dl[6], D = 0.0;
 #pragma unroll
@@ -231,6 +255,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
             for (int cc = r; cc < 6; cc++, q++) Hm[q] += k2 * s_rec[REC_H + q][jj] + gv[r] * gv[cc];  // :236-242
 #pragma unroll
           for (int d = 0; d < 6; d++) v[d] += gv[d] - kij * s_rec[REC_B + d][jj];  // :244 with b' = -b
+        }
         }
       }
 #pragma unroll
@@ -352,14 +377,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
   for (int l = gtid; l < a.P_l; l += gn) {
     const int p = a.p_lo + l;
     double d[6];
+#pragma unroll
     for (int i = 0; i < 6; i++) d[i] = a.delta[(size_t)l * 6 + i];
     double dR[9], Jl[9], R[9], Rn[9], dt[3], t[3], w[3];
     so3_exp(d + 3, dR, Jl);  // :269-271
+#pragma unroll
     for (int r = 0; r < 3; r++) dt[r] = Jl[3 * r] * d[0] + Jl[3 * r + 1] * d[1] + Jl[3 * r + 2] * d[2];  // :275
+#pragma unroll
     for (int i = 0; i < 9; i++) R[i] = a.R[9 * (size_t)p + i];
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
       for (int cc = 0; cc < 3; cc++) Rn[3 * r + cc] = R[3 * r] * dR[cc] + R[3 * r + 1] * dR[3 + cc] + R[3 * r + 2] * dR[6 + cc];  // :277
+#pragma unroll
     for (int i = 0; i < 9; i++) a.R[9 * (size_t)p + i] = Rn[i];
+#pragma unroll
     for (int r = 0; r < 3; r++) {
       t[r] = (Rn[3 * r] * dt[0] + Rn[3 * r + 1] * dt[1] + Rn[3 * r + 2] * dt[2]) + a.t[3 * (size_t)p + r];  // :278 (Q6)
       a.t[3 * (size_t)p + r] = t[r];
@@ -369,16 +401,24 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
     // head of the next iteration (k_prep): x = [t ; Log R], fp32 transforms relative to q0
     so3_log(Rn, w);
     double *rec = a.rec + (size_t)p * REC;
+#pragma unroll
     for (int i = 0; i < 3; i++) { rec[REC_X + i] = t[i]; rec[REC_X + 3 + i] = w[i]; }
     rec[REC_DNORM] = dn;
     double D[9], T[9], M[9];
+#pragma unroll
     for (int i = 0; i < 9; i++) D[i] = Rn[i] - ((i % 4 == 0) ? 1.0 : 0.0);
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
       for (int cc = 0; cc < 3; cc++) T[3 * r + cc] = R0[3 * r] * D[cc] + R0[3 * r + 1] * D[3 + cc] + R0[3 * r + 2] * D[6 + cc];
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
       for (int cc = 0; cc < 3; cc++) M[3 * r + cc] = T[3 * r] * R0[3 * cc] + T[3 * r + 1] * R0[3 * cc + 1] + T[3 * r + 2] * R0[3 * cc + 2];
     float *xf = ia.xf + (size_t)l * 12;
+#pragma unroll
     for (int i = 0; i < 9; i++) { const float f = __double2float_rn(M[i]); xf[i] = f; accc[i] += (double)f; }
+#pragma unroll
     for (int r = 0; r < 3; r++) {
       const float f = __double2float_rn(R0[3 * r] * t[0] + R0[3 * r + 1] * t[1] + R0[3 * r + 2] * t[2]);
       xf[9 + r] = f;
@@ -448,8 +488,12 @@ int launch_tail_fused(const SteinArgs &a, const IterArgs &ia, cudaStream_t st) {
   if (max_blocks_per_sm < 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, k_tail_fused, TF_THREADS, 0);
   if (max_blocks_per_sm < 1) return -1;
   int grid = a.sm_count;  // one CTA per SM: all co-resident, as the grid barriers require
-  void *args[] = {(void *)&a, (void *)&ia};
-  const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_tail_fused, dim3(grid), dim3(TF_THREADS), args, 0, st);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_tail_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024); attr = true; }
+  int xs_bytes = 6 * a.P * (int)sizeof(double);
+  if (xs_bytes > 160 * 1024 || a.P < 2) xs_bytes = 0;  // large P: read x through L2 instead
+  void *args[] = {(void *)&a, (void *)&ia, (void *)&xs_bytes};
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_tail_fused, dim3(grid), dim3(TF_THREADS), args, (size_t)xs_bytes, st);
   return e == cudaSuccess ? 1 : -1;
 }
 
