@@ -189,6 +189,69 @@ class Oracle:
         return out
 
 
+    # ---- SVGD-ICP class (svgd_oracle.c) ----
+    def svgd_align(self, prm: "SvgdParams", src, tgt, prev_pose, init_pose, R0, t0, dumps=()):
+        src, tgt, init_pose, prev_pose = _f64(src), _f64(tgt), _f64(init_pose), _f64(prev_pose)
+        P, I, ns = init_pose.shape[1], prm.iterations, len(src)
+        out = dict(particles=np.zeros((6, P)), mean=np.zeros(6), var=np.zeros(6), cov=np.zeros((6, 6)),
+                   weights=np.zeros(P), history=np.zeros((I, 6, P), dtype=np.float32))
+        shapes = dict(grad=((I, P, 6), np.float64), stein=((I, P, 6), np.float64), bandwidth=((I,), np.float64),
+                      x_after=((I, P, 6), np.float64), corr_idx=((I, P, ns), np.int32), corr_mask=((I, P, ns), np.uint8))
+        d = SvgdDumps()
+        for name in dumps:
+            shp, dt = shapes[name]
+            out[name] = np.zeros(shp, dtype=dt)
+            setattr(d, name, out[name].ctypes.data)
+        it = C.c_int(0)
+        with np.errstate(all="ignore"):
+            out["state"] = self.lib.oracle_svgd_align(
+                C.byref(prm), _ptr(src), C.c_int64(ns), _ptr(tgt), C.c_int64(len(tgt)), _ptr(prev_pose), _ptr(init_pose),
+                C.c_int(P), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(out["particles"]), _ptr(out["mean"]), _ptr(out["var"]),
+                _ptr(out["cov"]), _ptr(out["weights"]), _ptr(out["history"]), C.byref(it), C.byref(d))
+        out["iters_done"] = it.value
+        return out
+
+    def svgd_grad(self, poses, R0, t0, src, tgt, cand_idx, max_dist):
+        poses, src, tgt = _f64(poses), _f64(src), _f64(tgt)
+        cand_idx = np.ascontiguousarray(cand_idx, dtype=np.int64)
+        g = np.zeros((len(poses), 6))
+        self.lib.oracle_svgd_grad(_ptr(poses), C.c_int(len(poses)), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(src), C.c_int64(len(src)),
+                                  _ptr(tgt), _ptr(cand_idx), C.c_int(cand_idx.shape[1]), C.c_double(max_dist), _ptr(g))
+        return g
+
+    def svgd_step(self, x, g):
+        x, g = _f64(x), _f64(g)
+        out = np.zeros_like(x)
+        h = C.c_double(0)
+        self.lib.oracle_svgd_step(_ptr(x), _ptr(g), C.c_int(len(x)), _ptr(out), C.byref(h))
+        return out, h.value
+
+    def euler_R(self, r, p, y):
+        R = np.zeros(9)
+        self.lib.oracle_euler_R(C.c_double(r), C.c_double(p), C.c_double(y), _ptr(R))
+        return R.reshape(3, 3)
+
+
+OPTIMIZERS = {"Adam": 0, "RMSprop": 1, "SGD": 2, "Adagrad": 3}
+
+
+class SvgdParams(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("lr", C.c_double), ("max_dist", C.c_double),
+                ("check_early_stop", C.c_int), ("convergence_threshold", C.c_double),
+                ("knn_count", C.c_int), ("optimizer", C.c_int)]
+
+
+def make_svgd_params(iterations=30, lr=0.03, max_dist=3.0, check_early_stop=False, convergence_threshold=5e-4,
+                     knn_count=100, optimizer="Adam") -> SvgdParams:
+    return SvgdParams(int(iterations), float(lr), float(max_dist), int(bool(check_early_stop)),
+                      float(convergence_threshold), int(knn_count), OPTIMIZERS.get(optimizer, -1))
+
+
+class SvgdDumps(C.Structure):
+    _fields_ = [("grad", C.c_void_p), ("stein", C.c_void_p), ("bandwidth", C.c_void_p), ("x_after", C.c_void_p),
+                ("corr_idx", C.c_void_p), ("corr_mask", C.c_void_p)]
+
+
 def ref_available() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libsvnicp_ref.so"))
 
@@ -217,6 +280,20 @@ class Reference:
                                          _ptr(init_pose), C.c_int(P), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(out["particles"]),
                                          _ptr(out["mean"]), _ptr(out["var"]), _ptr(out["cov"]), _ptr(out["weights"]),
                                          _ptr(out["history"]), _ptr(out["seconds"]))
+        return out
+
+    def svgd_scan(self, prm: Params, optimizer: str, src, tgt, ctor_pose, init_pose, R0, t0, init_pose2=None):
+        """SVGDICP class: ctor(ctor_pose) -> add_cloud(init_pose) -> align [-> add_cloud(init_pose2) -> align]."""
+        src, tgt, init_pose, ctor_pose = _f64(src), _f64(tgt), _f64(init_pose), _f64(ctor_pose)
+        ip2 = _f64(init_pose2) if init_pose2 is not None else None
+        P, I = init_pose.shape[1], prm.iterations
+        out = dict(particles=np.zeros((6, P)), mean=np.zeros(6), var=np.zeros(6), cov=np.zeros((6, 6)),
+                   weights=np.zeros(P), history=np.zeros((I, 6, P), dtype=np.float32), runtime=np.zeros(3))
+        out["state"] = self.lib.ref_svgd_scan(C.byref(prm), optimizer.encode(), _ptr(src), C.c_int64(len(src)), _ptr(tgt),
+                                              C.c_int64(len(tgt)), _ptr(ctor_pose), _ptr(init_pose), _ptr(ip2), C.c_int(P),
+                                              _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(out["particles"]), _ptr(out["mean"]),
+                                              _ptr(out["var"]), _ptr(out["cov"]), _ptr(out["weights"]), _ptr(out["history"]),
+                                              _ptr(out["runtime"]))
         return out
 
     def scan_steps(self, prm: Params, src, tgt, init_pose, R0, t0, steps, want=("x_after", "H", "b", "tgt_paired", "cand_idx")):

@@ -208,4 +208,45 @@ int ref_scan_steps(const ref_params *prm, const double *src, int64_t n_s, const 
   return state;
 }
 
+// SVGD-ICP class through its public interface (SVGDICP.h:64-110).  ctor_pose is what the
+// constructor sees (it seeds pose_particles_, which add_cloud does not refresh), init_pose what
+// add_cloud sees.  Two consecutive scans when init_pose2 != NULL (same clouds), outputs from the last.
+int ref_svgd_scan(const ref_params *prm, const char *optimizer, const double *src, int64_t n_s, const double *tgt,
+                  int64_t n_t, const double *ctor_pose, const double *init_pose, const double *init_pose2, int P,
+                  const double *R0, const double *t0, double *particles, double *mean, double *var, double *cov,
+                  double *weights, float *history, double *runtime3) {
+  torch::NoGradGuard ng;
+  auto cfg = to_param(prm);
+  cfg.optimizer = optimizer;
+  const auto ctor = blob(ctor_pose, {6, P, 1});
+  svnicp::SVGDICP icp(cfg, ctor);
+  const auto s = blob(src, {n_s, 3}), t = blob(tgt, {n_t, 3});
+  int state = 0;
+  for (int scan = 0; scan < (init_pose2 ? 2 : 1); scan++) {
+    const auto init = blob(scan == 0 ? init_pose : init_pose2, {6, P, 1});
+    icp.add_cloud(s, t, init);
+    icp.set_initial_mean(*make_pose(R0, t0));
+    state = icp.stein_align();
+  }
+  const auto m = icp.get_transformation().contiguous();
+  const auto v = icp.get_distribution().contiguous();
+  const auto c = icp.get_cov_matrix();
+  const auto pp = icp.get_particles();
+  const auto w = icp.get_particle_weight();
+  std::memcpy(mean, m.data_ptr<double>(), 6 * sizeof(double));
+  std::memcpy(var, v.data_ptr<double>(), 6 * sizeof(double));
+  std::memcpy(cov, c.data(), 36 * sizeof(double));
+  std::memcpy(particles, pp.data(), sizeof(double) * 6 * P);
+  if (weights) std::memcpy(weights, w.data(), sizeof(double) * P);
+  if (history && state == 1) {
+    const auto h = icp.get_particle_history();
+    for (int i = 0; i < prm->iterations; i++) std::memcpy(history + (size_t)i * 6 * P, h[i].data(), sizeof(float) * 6 * P);
+  }
+  if (runtime3) {
+    const auto r = icp.get_runtime();
+    for (int i = 0; i < 3; i++) runtime3[i] = r[i];
+  }
+  return state;
+}
+
 }  // extern "C"
