@@ -44,8 +44,8 @@ def _ptr(a):
 
 def build(force: bool = False) -> str:
     so = os.path.join(HERE, "liboracle.so")
-    src = os.path.join(HERE, "svn_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("svn_oracle.c", "svgd_oracle.c")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -218,6 +218,25 @@ class Oracle:
         self.lib.oracle_svgd_grad(_ptr(poses), C.c_int(len(poses)), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(src), C.c_int64(len(src)),
                                   _ptr(tgt), _ptr(cand_idx), C.c_int(cand_idx.shape[1]), C.c_double(max_dist), _ptr(g))
         return g
+
+    def svgd_grad_given_corr(self, poses, R0, t0, src, tgt, corr_idx, corr_mask, max_dist):
+        poses, src, tgt = _f64(poses), _f64(src), _f64(tgt)
+        corr_idx = np.ascontiguousarray(corr_idx, dtype=np.int32)
+        corr_mask = np.ascontiguousarray(corr_mask, dtype=np.uint8)
+        g = np.zeros((len(poses), 6))
+        self.lib.oracle_svgd_grad_given_corr(_ptr(poses), C.c_int(len(poses)), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(src),
+                                             C.c_int64(len(src)), _ptr(tgt), _ptr(corr_idx), _ptr(corr_mask),
+                                             C.c_double(max_dist), _ptr(g))
+        return g
+
+    def svgd_corr(self, poses, R0, t0, src, tgt, cand_idx, max_dist):
+        poses, src, tgt = _f64(poses), _f64(src), _f64(tgt)
+        cand_idx = np.ascontiguousarray(cand_idx, dtype=np.int64)
+        idx = np.zeros((len(poses), len(src)), dtype=np.int32)
+        mask = np.zeros((len(poses), len(src)), dtype=np.uint8)
+        self.lib.oracle_svgd_corr(_ptr(poses), C.c_int(len(poses)), _ptr(_f64(R0)), _ptr(_f64(t0)), _ptr(src), C.c_int64(len(src)),
+                                  _ptr(tgt), _ptr(cand_idx), C.c_int(cand_idx.shape[1]), C.c_double(max_dist), _ptr(idx), _ptr(mask))
+        return idx, mask
 
     def svgd_step(self, x, g):
         x, g = _f64(x), _f64(g)

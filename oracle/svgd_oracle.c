@@ -79,7 +79,8 @@ static void m3mul(const double *A, const double *B, double *C) {
  * gradient_scaling_factor_ = N_s (:58, :454). */
 static void particle_sgd_grad(const double pose[6], const double R0[9], const double t0[3], const double *src,
                               int64_t n_s, const double *tgt, const int64_t *cand, int K, double max_dist,
-                              double out[6], int32_t *corr_out, uint8_t *mask_out) {
+                              double out[6], int32_t *corr_out, uint8_t *mask_out, const int32_t *given_idx,
+                              const uint8_t *given_mask) {
   double R[9], Rt[9], tt[3], dR[27], M[27];
   oracle_euler_R(pose[3], pose[4], pose[5], R);                    /* :88 */
   m3mul(R0, R, Rt);                                                /* :90 */
@@ -94,14 +95,21 @@ static void particle_sgd_grad(const double pose[6], const double R0[9], const do
     for (int r = 0; r < 3; r++) q[r] = Rt[3 * r] * s[0] + Rt[3 * r + 1] * s[1] + Rt[3 * r + 2] * s[2] + tt[r]; /* :94 */
     double best = 0;
     int bestk = -1;
-    for (int k = 0; k < K; k++) {                                  /* knn.cu 1-NN, strict '<' */
-      const double *m = tgt + 3 * cand[i * K + k];
-      double dx = q[0] - m[0], dy = q[1] - m[1], dz = q[2] - m[2];
-      double d = fma(dz, dz, fma(dy, dy, dx * dx));
-      if (bestk < 0 || d < best) { best = d; bestk = k; }
+    int64_t gi;
+    double mu;
+    if (given_idx) {                                               /* test mode: correspondences chosen elsewhere */
+      gi = given_idx[i];
+      mu = given_mask[i] ? 1.0 : 0.0;
+    } else {
+      for (int k = 0; k < K; k++) {                                /* knn.cu 1-NN, strict '<' */
+        const double *m = tgt + 3 * cand[i * K + k];
+        double dx = q[0] - m[0], dy = q[1] - m[1], dz = q[2] - m[2];
+        double d = fma(dz, dz, fma(dy, dy, dx * dx));
+        if (bestk < 0 || d < best) { best = d; bestk = k; }
+      }
+      gi = cand[i * K + bestk];
+      mu = (best < max_dist) ? 1.0 : 0.0;                          /* :332 (Q1) */
     }
-    const int64_t gi = cand[i * K + bestk];
-    const double mu = (best < max_dist) ? 1.0 : 0.0;               /* :332 (Q1) */
     if (corr_out) corr_out[i] = (int32_t)gi;
     if (mask_out) mask_out[i] = (uint8_t)mu;
     double sp[3] = {mu * s[0], mu * s[1], mu * s[2]};
@@ -239,7 +247,7 @@ int oracle_svgd_align(const oracle_svgd_params *prm, const double *src, int64_t 
     for (int p = 0; p < P; p++) {
       int32_t *co = (dmp && dmp->corr_idx) ? dmp->corr_idx + ((size_t)epoch * P + p) * n_s : NULL;
       uint8_t *mo = (dmp && dmp->corr_mask) ? dmp->corr_mask + ((size_t)epoch * P + p) * n_s : NULL;
-      particle_sgd_grad(x + 6 * p, R0, t0, src, n_s, tgt, cand, K, prm->max_dist, grad + 6 * p, co, mo); /* :106 */
+      particle_sgd_grad(x + 6 * p, R0, t0, src, n_s, tgt, cand, K, prm->max_dist, grad + 6 * p, co, mo, NULL, NULL); /* :106 */
     }
     double h = 0;
     for (int i = 0; i < 6 * P; i++) gneg[i] = -grad[i];
@@ -280,5 +288,27 @@ void oracle_svgd_grad(const double *poses, int P, const double R0[9], const doub
                       int64_t n_s, const double *tgt, const int64_t *cand, int K, double max_dist, double *grad) {
 #pragma omp parallel for schedule(dynamic, 1)
   for (int p = 0; p < P; p++)
-    particle_sgd_grad(poses + 6 * p, R0, t0, src, n_s, tgt, cand, K, max_dist, grad + 6 * p, NULL, NULL);
+    particle_sgd_grad(poses + 6 * p, R0, t0, src, n_s, tgt, cand, K, max_dist, grad + 6 * p, NULL, NULL, NULL, NULL);
+}
+
+/* same, on GIVEN correspondences (corr_idx [P][n_s] global map index, corr_mask [P][n_s]): separates the arithmetic of the
+ * gradient from fp32-vs-fp64 near-tie / near-threshold decisions; corr_out/mask_out optional [P][n_s] = the fp64 choices */
+void oracle_svgd_grad_given_corr(const double *poses, int P, const double R0[9], const double t0[3], const double *src,
+                                 int64_t n_s, const double *tgt, const int32_t *corr_idx, const uint8_t *corr_mask,
+                                 double max_dist, double *grad) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int p = 0; p < P; p++)
+    particle_sgd_grad(poses + 6 * p, R0, t0, src, n_s, tgt, NULL, 0, max_dist, grad + 6 * p, NULL, NULL,
+                      corr_idx + (size_t)p * n_s, corr_mask + (size_t)p * n_s);
+}
+
+/* the fp64 correspondences alone, for flip statistics */
+void oracle_svgd_corr(const double *poses, int P, const double R0[9], const double t0[3], const double *src, int64_t n_s,
+                      const double *tgt, const int64_t *cand, int K, double max_dist, int32_t *corr_idx, uint8_t *corr_mask) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int p = 0; p < P; p++) {
+    double g[6];
+    particle_sgd_grad(poses + 6 * p, R0, t0, src, n_s, tgt, cand, K, max_dist, g, corr_idx + (size_t)p * n_s,
+                      corr_mask + (size_t)p * n_s, NULL, NULL);
+  }
 }

@@ -342,3 +342,20 @@ class SVNICP:
         v = C.c_int64(0)
         self._check(self._lib.svnicp_get_launch_count(self._h, C.byref(v)), "get_launch_count")
         return v.value
+
+
+NO_OPTIMIZER = 2  # SteinICPState, SVGDICP.h:59-62
+
+
+class SVGDICP(SVNICP):
+    """Drop-in for svnicp::SVGDICP (SVGDICP.h:64-211, the `class_type: SVGDICP` branch of OdometryPipeline.cpp:282-288):
+    Euler-angle particles, first-order gradient, RBF SVGD step, Adam / RMSprop / SGD / Adagrad update.  Same interface
+    and device pipeline as SVNICP (in the reference SVNICP derives from SVGDICP; here the two share one handle type and
+    differ by class_type).  stein_align returns NO_OPTIMIZER (2) for an unknown optimizer name, like the reference.
+    Note the reference quirk kept here: the particle set given to the CONSTRUCTOR is what iteration 0 of the first
+    scan evaluates the kernel on (add_cloud does not refresh pose_particles_, SVGDICP.cpp:46-62)."""
+
+    class_type = CLASS_SVGDICP
+
+    def __init__(self, param: SteinICPParam, init_pose, device: int = -1):
+        super().__init__(param, init_pose, None, device)

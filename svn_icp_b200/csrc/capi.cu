@@ -90,6 +90,9 @@ struct svnicp_handle_t {
   // device buffers
   DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, rec, xs, delta, Hbar_inv, stats, particles, init_pose, prep_scratch_d;
   DevBuf<int> prep_scratch_i;
+  // SVGD-ICP class state (class_type = SVGDICP): parameters, pose_particles_ carried between scans, optimizer moments
+  DevBuf<double> pose6, prev, opt_state;
+  int optimizer = -1;
   DevBuf<float4> sp, cand, clist, spair;
   int pair_mode = 0;
   int rows_per_rank = 0;
@@ -185,12 +188,25 @@ static void set_slice(svnicp_handle h) {
   h->P_l = hi > h->p_lo ? hi - h->p_lo : 0;
 }
 
+static SvgdArgs svgd_args(svnicp_handle h) {
+  SvgdArgs s;
+  s.P = h->P; s.p_lo = h->p_lo; s.P_l = h->P_l;
+  s.optimizer = h->optimizer; s.lr = h->prm.lr;
+  s.pose6 = h->pose6.p; s.prev = h->prev.p; s.opt_state = h->opt_state.p;
+  return s;
+}
+
 static int upload_particles(svnicp_handle h, const double *init_pose) {
   const size_t n = (size_t)6 * h->P;
   CU(h->init_pose.ensure(n));
   if (init_pose) CU(cudaMemcpyAsync(h->init_pose.p, init_pose, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   else CU(cudaMemsetAsync(h->init_pose.p, 0, n * sizeof(double), h->stream));
-  launch_init_particles(h->R.p, h->t.p, h->init_pose.p, h->P, h->dnorm.p, h->p_lo, h->P_l, h->ctrl.p, h->stream);
+  if (h->class_type == SVNICP_CLASS_SVGDICP) {
+    SvgdArgs s = svgd_args(h);
+    launch_svgd_init(s, h->init_pose.p, h->R.p, h->t.p, h->dnorm.p, h->ctrl.p, h->stream);
+  } else {
+    launch_init_particles(h->R.p, h->t.p, h->init_pose.p, h->P, h->dnorm.p, h->p_lo, h->P_l, h->ctrl.p, h->stream);
+  }
   CU(cudaGetLastError());
   // the copy source is caller memory: finish before returning (the reference clones synchronously too)
   CU(cudaStreamSynchronize(h->stream));
@@ -217,7 +233,23 @@ static int alloc_particle_state(svnicp_handle h) {
   const size_t I = (size_t)(h->prm.iterations > 0 ? h->prm.iterations : 1);
   CU(h->history.ensure(I * 6 * h->P));
   CU(h->kept_hist.ensure(I + 2, true));
+  if (h->class_type == SVNICP_CLASS_SVGDICP) {
+    CU(h->pose6.ensure(6 * P, true));
+    CU(h->prev.ensure(6 * P, true));
+    CU(h->opt_state.ensure(12 * (size_t)(h->P_l_max > 0 ? h->P_l_max : 1), true));
+  }
   return SVNICP_OK;
+}
+
+static int parse_optimizer(const char *name) {  // SVGDICP.cpp:142-170
+  char buf[17];
+  memcpy(buf, name, 16);
+  buf[16] = 0;
+  if (!strcmp(buf, "Adam")) return SVGD_OPT_ADAM;
+  if (!strcmp(buf, "RMSprop")) return SVGD_OPT_RMSPROP;
+  if (!strcmp(buf, "SGD")) return SVGD_OPT_SGD;
+  if (!strcmp(buf, "Adagrad")) return SVGD_OPT_ADAGRAD;
+  return -1;  // "No optimizer chosen": stein_align returns NO_OPTIMIZER
 }
 
 int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_count, const double *init_pose, int class_type,
@@ -225,8 +257,10 @@ int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_
   if (!out || !params) return fail(nullptr, SVNICP_ERR_INVALID, "null argument");
   *out = nullptr;
   if (particle_count < 1) return fail(nullptr, SVNICP_ERR_INVALID, "particle_count must be >= 1");
-  if (class_type != SVNICP_CLASS_SVNICP)
-    return fail(nullptr, SVNICP_ERR_INVALID, "class_type SVGDICP (first-order path, SURVEY.md 8(f) row 2) is not built yet");
+  if (class_type != SVNICP_CLASS_SVNICP && class_type != SVNICP_CLASS_SVGDICP)
+    return fail(nullptr, SVNICP_ERR_INVALID, "class_type must be SVNICP_CLASS_SVNICP or SVNICP_CLASS_SVGDICP");
+  if (params->use_minibatch)
+    return fail(nullptr, SVNICP_ERR_INVALID, "use_minibatch is not supported (the reference never enables it, SVGDICP.cpp:178-185)");
   if (params->KNN_count < 1 || params->KNN_count > 256) return fail(nullptr, SVNICP_ERR_INVALID, "KNN_count must be in [1,256]");
   if (params->iterations < 0) return fail(nullptr, SVNICP_ERR_INVALID, "iterations must be >= 0");
   int ndev = 0;
@@ -240,6 +274,7 @@ int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_
   svnicp_handle h = new svnicp_handle_t();
   h->prm = *params;
   h->class_type = class_type;
+  h->optimizer = parse_optimizer(params->optimizer);
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->P = particle_count;
@@ -264,6 +299,13 @@ int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_
     CU(cudaMallocHost((void **)&h->h_ctrl, sizeof(Ctrl)));
     memset(h->h_stats, 0, 48 * sizeof(double));
     memset(h->h_particles, 0, (size_t)6 * h->P * sizeof(double));
+    if (h->class_type == SVNICP_CLASS_SVGDICP && init_pose) {
+      // pose_particles_ as the constructor leaves it (SVGDICP.cpp:33-35): add_cloud never refreshes it
+      std::vector<double> pp((size_t)6 * h->P);
+      for (int p = 0; p < h->P; p++)
+        for (int c = 0; c < 6; c++) pp[(size_t)p * 6 + c] = init_pose[(size_t)c * h->P + p];
+      CU(cudaMemcpy(h->prev.p, pp.data(), pp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     return upload_particles(h, init_pose);
   };
   rc = body();
@@ -282,7 +324,7 @@ void svnicp_destroy(svnicp_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   DevBuf<double> *d[] = {&h->src64, &h->tgt64, &h->q0, &h->sxyz, &h->R, &h->t, &h->dnorm, &h->part, &h->rec, &h->xs, &h->delta,
-                         &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose, &h->prep_scratch_d};
+                         &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose, &h->prep_scratch_d, &h->pose6, &h->prev, &h->opt_state};
   h->prep_scratch_i.release();
   for (auto *b : d) b->release();
   h->sp.release(); h->cand.release(); h->clist.release(); h->spair.release();
@@ -358,7 +400,7 @@ static int choose_shape(svnicp_handle h) {
   // (gn_pair.cu, 512 threads, one CTA per SM; needs >= 32 local particles so a warp shares a source point).  Measured at
   // configs[1]: pair mode issues 33 % fewer instructions but is not faster (32.7 vs 30.6 ms of k_gn per scan) because
   // FFMA2 delivers the same 32 results/clk/SMSP as scalar FFMA (scripts/micro/ffma2_bench.cu) -- see DESIGN.md.
-  h->pair_mode = (h->P_l >= 32 && getenv("SVNICP_GN_PAIR")) ? 1 : 0;
+  h->pair_mode = (h->P_l >= 32 && getenv("SVNICP_GN_PAIR") && h->class_type == SVNICP_CLASS_SVNICP) ? 1 : 0;
   const int consumers = h->pair_mode ? 512 : 256;
   if (h->pair_mode && !getenv("SVNICP_GN_SMEM_KB")) budget = 160 * 1024;
   while (TB > (h->pair_mode ? 8 : 4) && gn_stage_bytes(TB, Kp) * S > budget) TB >>= 1;
@@ -482,6 +524,28 @@ int svnicp_align(svnicp_handle h) {
   CU(cudaMemsetAsync(h->history.p, 0, (size_t)(I > 0 ? I : 1) * 6 * h->P * sizeof(float), st));  // SVGDICP.cpp:172-174
   CU(cudaMemsetAsync(h->kept_hist.p, 0, ((size_t)I + 2) * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(h->misc.p, 0, 8 * sizeof(int), st));
+  const bool svgd = h->class_type == SVNICP_CLASS_SVGDICP;
+  const SvgdArgs sv = svgd ? svgd_args(h) : SvgdArgs();
+  if (svgd && h->optimizer < 0) {
+    // SVGDICP.cpp:73-75: "No optimizer chosen" -> NO_OPTIMIZER before anything moves; the getters then describe the
+    // untouched pose_particles_ (every rank holds all of it)
+    SteinArgs sa0;
+    memset(&sa0, 0, sizeof(sa0));
+    sa0.P = h->P; sa0.rec = h->rec.p; sa0.stats = h->stats.p; sa0.particles = h->particles.p;
+    h->launches += launch_svgd_rec(h->rec.p, h->prev.p, nullptr, 0, h->P, 0, st);
+    h->launches += launch_stats_svgd(sa0, nullptr, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->h_stats, h->stats.p, 48 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_particles, h->particles.p, (size_t)6 * h->P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memset(h->h_ctrl, 0, sizeof(Ctrl));
+    memset(h->h_kept, 0, ((size_t)I + 2) * sizeof(unsigned long long));
+    h->iters_done = 0;
+    h->enqueued_iters = 0;
+    h->ms_setup = h->ms_iter = h->ms_epi = h->ms_total = 0;
+    h->aligned = true;
+    return SVNICP_NO_OPTIMIZER;
+  }
 
   CU(cudaEventRecord(h->ev[0], st));
   // ---- per-scan setup: candidate table (SVGDICP.cpp:176-215) ----
@@ -524,6 +588,7 @@ int svnicp_align(svnicp_handle h) {
   ia.R = h->R.p; ia.t = h->t.p; ia.xf = h->xf.p; ia.dnorm = h->dnorm.p; ia.part = h->part.p; ia.rec = h->rec.p; ia.ctrl = h->ctrl.p;
   ia.TB = h->TB; ia.stages = h->stages; ia.n_slices = h->n_slices; ia.n_pgroups = h->n_pgroups; ia.PG = h->PG; ia.RG = h->RG;
   ia.gn_smem = h->gn_smem; ia.sm_count = h->sm_count; ia.svn_full_grad = h->prm.SVN_full_grad;
+  ia.first_order = svgd ? 1 : 0;
   ia.dbg_idx = h->prm.debug_corr ? h->dbg_idx.p : nullptr;
   ia.dbg_mask = h->prm.debug_corr ? h->dbg_mask.p : nullptr;
 
@@ -540,7 +605,7 @@ int svnicp_align(svnicp_handle h) {
   sa.prep_scratch_i = h->prep_scratch_i.p;
   // one cooperative kernel per iteration for decide + median + Stein + update + next prep (tail_fused.cu);
   // SVNICP_NO_FUSED_TAIL=1 keeps the nine separate launches (A/B measurements, same-bits test)
-  const bool fused_tail = getenv("SVNICP_NO_FUSED_TAIL") == nullptr;
+  const bool fused_tail = !svgd && getenv("SVNICP_NO_FUSED_TAIL") == nullptr;
 
   if (h->profile)
     while (h->prof_events.size() < (size_t)I * 7) {
@@ -569,7 +634,7 @@ int svnicp_align(svnicp_handle h) {
       CU(cudaMemcpyAsync(h->dbg_xf.p, h->xf.p, (size_t)h->P_l * 12 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     PROF(3);
-    h->launches += launch_finalize(ia, st);
+    h->launches += svgd ? launch_finalize_first(ia, sv, st) : launch_finalize(ia, st);
     PROF(4);
     int rc = do_allgather(h);
     if (rc) return rc;
@@ -581,8 +646,13 @@ int svnicp_align(svnicp_handle h) {
     } else {
       h->launches += launch_decide(sa, st, 0);
       h->launches += launch_median(sa, st);
-      h->launches += launch_stein(sa, st);
-      h->launches += launch_update(sa, st);
+      if (svgd) {
+        h->launches += launch_stein_first(sa, st);
+        h->launches += launch_update_opt(sa, sv, e + 1, st);
+      } else {
+        h->launches += launch_stein(sa, st);
+        h->launches += launch_update(sa, st);
+      }
     }
     PROF(6);
 #undef PROF
@@ -595,13 +665,14 @@ int svnicp_align(svnicp_handle h) {
   h->enqueued_iters = e;
   CU(cudaEventRecord(h->ev[2], st));
   // ---- epilogue: final x, last stop decision / history row, getters (SVNICP.cpp:111, :281-308) ----
-  h->launches += launch_prep(ia, st, 1);
+  if (svgd) h->launches += launch_svgd_rec(h->rec.p, h->pose6.p, h->dnorm.p, h->p_lo, h->P_l, h->p_lo, st);
+  else h->launches += launch_prep(ia, st, 1);
   {
     int rc = do_allgather(h);
     if (rc) return rc;
   }
   h->launches += launch_decide(sa, st, 1);
-  h->launches += launch_stats(sa, st);
+  h->launches += svgd ? launch_stats_svgd(sa, h->prev.p, st) : launch_stats(sa, st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(h->h_stats, h->stats.p, 48 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h->h_particles, h->particles.p, (size_t)6 * h->P * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -658,7 +729,8 @@ int svnicp_get_particles(svnicp_handle h, double *out) {
 }
 int svnicp_get_particle_weight(svnicp_handle h, double *out) {
   if (!h) return SVNICP_ERR_INVALID;
-  const double w = (double)(1.0f / (float)h->P);  // SVNICP.cpp:46 + :281-284: float32 weights widened to double
+  // SVNICP.cpp:46 + :281-284: float32 weights widened to double; SVGDICP.cpp:522-524: a vector of ones
+  const double w = h->class_type == SVNICP_CLASS_SVGDICP ? 1.0 : (double)(1.0f / (float)h->P);
   for (int p = 0; p < h->P; p++) out[p] = w;
   return SVNICP_OK;
 }

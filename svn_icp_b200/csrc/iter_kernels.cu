@@ -270,7 +270,10 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 // UNI: every lane of a warp works on the same source point (PG >= 32) -> the early exit is a warp vote.
-template <bool DBG, bool UNI>
+// FIRST: first-order mode of the SVGD-ICP class (SVGDICP::sgd_grad, SVGDICP.cpp:398-455): sum 0 counts the unmasked
+// pairs (nonzero_count, :404) and the second-moment sums 1..9 are not needed -- the gradient is E and C alone because
+// every Euler partial is [omega_k]x R (see svgd_class.cu).
+template <bool DBG, bool UNI, bool FIRST>
 __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a) {  // (.., 3) spills the fp64 accumulators: measured slower
   if (a.ctrl->stop) return;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -405,11 +408,15 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
           const float wq = Dm * rcp_approx(fmaf(3.0f, en, Dm));
           const float rho = wq * wq;
           const float rp = valid ? rho : 0.0f;
-          acc[0] += valid ? rho : 1.0f;
-          const float gx = rp * sv.x, gy = rp * sv.y, gz = rp * sv.z;
-          acc[1] += gx; acc[2] += gy; acc[3] += gz;
-          acc[4] = fmaf(gx, sv.x, acc[4]); acc[5] = fmaf(gx, sv.y, acc[5]); acc[6] = fmaf(gx, sv.z, acc[6]);
-          acc[7] = fmaf(gy, sv.y, acc[7]); acc[8] = fmaf(gy, sv.z, acc[8]); acc[9] = fmaf(gz, sv.z, acc[9]);
+          if (FIRST) {
+            acc[0] += valid ? 1.0f : 0.0f;
+          } else {
+            acc[0] += valid ? rho : 1.0f;
+            const float gx = rp * sv.x, gy = rp * sv.y, gz = rp * sv.z;
+            acc[1] += gx; acc[2] += gy; acc[3] += gz;
+            acc[4] = fmaf(gx, sv.x, acc[4]); acc[5] = fmaf(gx, sv.y, acc[5]); acc[6] = fmaf(gx, sv.z, acc[6]);
+            acc[7] = fmaf(gy, sv.y, acc[7]); acc[8] = fmaf(gy, sv.z, acc[8]); acc[9] = fmaf(gz, sv.z, acc[9]);
+          }
           const float fx = rp * ex, fy = rp * ey, fz = rp * ez;  // multiplication (not select): NaN must propagate
           acc[10] += fx; acc[11] += fy; acc[12] += fz;
           const float wx = ax + sv.x, wy = ay + sv.y, wz = az + sv.z;  // R~ s in the world-oriented frame
@@ -538,10 +545,10 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a) {
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 void init_iter_kernels() {
-  cudaFuncSetAttribute(k_gn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_gn<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_gn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_gn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+#define SVN_GN_ATTR(D, U, F) cudaFuncSetAttribute(k_gn<D, U, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+  SVN_GN_ATTR(false, true, false); SVN_GN_ATTR(true, true, false); SVN_GN_ATTR(false, false, false); SVN_GN_ATTR(true, false, false);
+  SVN_GN_ATTR(false, true, true); SVN_GN_ATTR(true, true, true); SVN_GN_ATTR(false, false, true); SVN_GN_ATTR(true, false, true);
+#undef SVN_GN_ATTR
 }
 
 int launch_prep(const IterArgs &a, cudaStream_t st, int x_only) {
@@ -571,13 +578,15 @@ int launch_filter(const IterArgs &a, cudaStream_t st) {
 int launch_gn(const IterArgs &a, cudaStream_t st) {
   dim3 grid(a.n_slices, a.n_pgroups);
   const bool uni = a.PG >= 32;
-  if (a.dbg_idx) {
-    if (uni) k_gn<true, true><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
-    else k_gn<true, false><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
+#define SVN_GN_GO(D, U, F) k_gn<D, U, F><<<grid, GN_THREADS, a.gn_smem, st>>>(a)
+  if (a.first_order) {
+    if (a.dbg_idx) { if (uni) SVN_GN_GO(true, true, true); else SVN_GN_GO(true, false, true); }
+    else { if (uni) SVN_GN_GO(false, true, true); else SVN_GN_GO(false, false, true); }
   } else {
-    if (uni) k_gn<false, true><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
-    else k_gn<false, false><<<grid, GN_THREADS, a.gn_smem, st>>>(a);
+    if (a.dbg_idx) { if (uni) SVN_GN_GO(true, true, false); else SVN_GN_GO(true, false, false); }
+    else { if (uni) SVN_GN_GO(false, true, false); else SVN_GN_GO(false, false, false); }
   }
+#undef SVN_GN_GO
   return 1;
 }
 

@@ -55,6 +55,7 @@ struct IterArgs {
   size_t gn_smem;
   int sm_count;
   int svn_full_grad;
+  int first_order;     // 1: SVGD-ICP class -- k_gn sums the first-order quantities only (svgd_class.cu)
   // debug taps (may be null)
   int32_t *dbg_idx;
   uint8_t *dbg_mask;
@@ -101,5 +102,23 @@ int launch_update(const SteinArgs &a, cudaStream_t st);
 int launch_stats(const SteinArgs &a, cudaStream_t st);
 int launch_init_particles(double *R, double *t, const double *init_pose_dev, int P, double *dnorm, int p_lo, int P_l, Ctrl *ctrl,
                           cudaStream_t st);
+
+
+// ---- SVGD-ICP class (class_type = SVGDICP, svgd_class.cu): first-order gradient + torch::optim-style update ----
+enum { SVGD_OPT_ADAM = 0, SVGD_OPT_RMSPROP = 1, SVGD_OPT_SGD = 2, SVGD_OPT_ADAGRAD = 3 };
+struct SvgdArgs {
+  int P, p_lo, P_l;
+  int optimizer;       // SVGD_OPT_*
+  double lr;
+  double *pose6;       // [P_pad][6] the parameters x_,y_,z_,rx_,ry_,rz_ (global particle index; local slice is live)
+  double *prev;        // [P][6] pose_particles_ as stein_align finds it (constructor / previous scan; SVGDICP.cpp:46-62)
+  double *opt_state;   // [P_l][12] optimizer moments, zeroed per scan (SVGDICP.cpp:73)
+};
+int launch_svgd_init(const SvgdArgs &s, const double *init_pose_dev, double *R, double *t, double *dnorm, Ctrl *ctrl, cudaStream_t st);
+int launch_finalize_first(const IterArgs &a, const SvgdArgs &s, cudaStream_t st);
+int launch_svgd_rec(double *rec, const double *src6, const double *dnorm, int lo, int n, int dn_off, cudaStream_t st);
+int launch_stein_first(const SteinArgs &a, cudaStream_t st);
+int launch_update_opt(const SteinArgs &a, const SvgdArgs &s, int step, cudaStream_t st);
+int launch_stats_svgd(const SteinArgs &a, double *prev_out, cudaStream_t st);
 
 }  // namespace svn

@@ -76,6 +76,9 @@ inline std::vector<double> initialize_particles_gaussian(int particle_count, con
 
 class SVGDICP {  // the base interface the node holds (OdometryPipeline.h:125)
  public:
+  /** SVGDICP::SVGDICP (SVGDICP.cpp:22-44): the first-order class itself (`class_type: SVGDICP`, OdometryPipeline.cpp:282-288) */
+  explicit SVGDICP(const SteinICPParam &parameters, const std::vector<double> &init_pose, int device = -1)
+      : SVGDICP(parameters, init_pose, ParticleWeightOpt{}, SVNICP_CLASS_SVGDICP, device) {}
   virtual ~SVGDICP() {
     if (h_) svnicp_destroy(h_);
   }

@@ -18,9 +18,10 @@ def oracle():
     return orc.Oracle()
 
 
-def golden_names():
+def golden_names(prefix="svn_"):
+    """svn_* = SVN-ICP class fixtures, svgd_* = SVGD-ICP class fixtures (different keys)."""
     d = os.path.join(ROOT, "tests", "golden")
-    return sorted(f[:-4] for f in os.listdir(d) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(d) if f.endswith(".npz") and f.startswith(prefix))
 
 
 def load_golden(name):

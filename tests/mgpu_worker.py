@@ -21,11 +21,18 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for P, full, es in ((96, True, False), (37, False, False), (64, True, True)):
+    cases = ((96, True, False, "svn"), (37, False, False, "svn"), (64, True, True, "svn"), (48, True, False, "svgd"), (41, True, True, "svgd"))
+    for P, full, es, cls in cases:
         pb = synth.make_problem(P, sensor="32", scan_index=6, n_map_scans=6, seed=0xC0FFEE)
-        prm = sv.SteinICPParam(iterations=10, KNN_count=64, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
-                               convergence_threshold=2e-3)
-        icp = sv.SVNICP(prm, pb.init_pose, device=local)
+        if cls == "svn":
+            prm = sv.SteinICPParam(iterations=10, KNN_count=64, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
+                                   convergence_threshold=1e-2)
+            make = lambda: sv.SVNICP(prm, pb.init_pose, device=local)
+        else:  # the SVGD-ICP class shards the same way (first-order record, same all-gather)
+            prm = sv.SteinICPParam(iterations=10, KNN_count=64, max_dist=3.0, lr=0.03, optimizer="Adam", check_early_stop=es,
+                                   convergence_threshold=6e-2)
+            make = lambda: sv.SVGDICP(prm, pb.init_pose, device=local)
+        icp = make()
         uid = [sv.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         icp.init_sharding(uid[0], rank, world)
@@ -42,13 +49,13 @@ def main():
         dist.broadcast(ref, src=0)
         same = bool(torch.equal(t, ref))
         if rank == 0:
-            single = sv.SVNICP(prm, pb.init_pose, device=local)
+            single = make()
             single.add_cloud(pb.source, pb.target, pb.init_pose)
             single.set_initial_mean(pb.R0, pb.t0)
             single.stein_align()
             err = np.abs(single.get_particles() - got).max()
             herr = np.abs(single.get_particle_history() - hist).max()
-            print(f"P={P} full={full} es={es} ranks={world}: |sharded - single| particles {err:.3e} history {herr:.3e} "
+            print(f"{cls} P={P} full={full} es={es} ranks={world}: |sharded - single| particles {err:.3e} history {herr:.3e} "
                   f"iters {its} vs {single.iterations_done()}", flush=True)
             # identical algorithm; only the grouping of the fp32 Gauss-Newton partial sums differs with the slice size
             ok &= err < 1e-7 and herr < 1e-6 and its == single.iterations_done()
