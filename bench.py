@@ -336,6 +336,26 @@ def main():
         variants["early_stop_thr5e-4_max100"] = dict(scans_per_sec=args.steps / (ms_es * 1e-3), ms_per_scan=ms_es / args.steps,
                                                      iterations_executed=icp_es.iterations_done())
         icp_es.close()
+        # the other registration class behind the same interface (class_type = SVGDICP): same scan,
+        # same particle count, the reference's shipped SVGD settings (Adam, lr 0.03; stein_icp params)
+        prm_gd = sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=WORKLOAD["max_dist"], lr=0.03, optimizer="Adam", check_early_stop=False)
+        icp_gd = sv.SVGDICP(prm_gd, particles[0], device=local_rank)
+        icp_gd.set_stream(stream.cuda_stream)
+
+        def scan_gd(i):
+            icp_gd.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, particles[i])
+            icp_gd.set_initial_mean(pb.R0, pb.t0)
+            icp_gd.stein_align()
+            return icp_gd.get_transformation()
+
+        scan_gd(0)
+        ms_gd, mean_gd = timed(scan_gd, 1, args.steps)
+        icp_gd.set_profiling(True)
+        scan_gd(1)
+        ph_gd = icp_gd.get_phase_times()
+        variants["svgd_icp_class_adam"] = dict(scans_per_sec=args.steps / (ms_gd * 1e-3), ms_per_scan=ms_gd / args.steps,
+                                               phases_ms_per_scan=ph_gd, mean=[float(v) for v in mean_gd])
+        icp_gd.close()
 
     if rank == 0:
         h2d = (n_s + n_t) * 24 + 6 * P * 8

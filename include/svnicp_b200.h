@@ -79,7 +79,13 @@ void svnicp_default_params(svnicp_params *p);
 int svnicp_abi_version(void);
 
 /* SVNICP::SVNICP / SVGDICP::SVGDICP (SVNICP.cpp:20-38, SVGDICP.cpp:22-44).
- * init_pose: [6][P] host doubles, may be NULL (zeros).  device: CUDA ordinal (-1 = current). */
+ * init_pose: [6][P] host doubles, may be NULL (zeros).  device: CUDA ordinal (-1 = current).
+ * class_type SVNICP_CLASS_SVNICP: particles are [t ; Log R] (axis-angle), Gauss-Newton + Stein Variational Newton step.
+ * class_type SVNICP_CLASS_SVGDICP: particles are (x,y,z,roll,pitch,yaw) ZYX Euler (SVGDICP.cpp:226-260), first-order
+ *   gradient (:398-455), RBF SVGD step (:457-474), params->optimizer update (:142-170, :476-494); svnicp_align returns
+ *   SVNICP_NO_OPTIMIZER for an unknown optimizer name.  The constructor's init_pose seeds pose_particles_, which
+ *   add_cloud does not refresh (:46-62): iteration 0 of a scan evaluates the kernel on the previous result.
+ * use_minibatch != 0 is rejected (the reference never enables it, :178-185). */
 int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_count, const double *init_pose,
                   int class_type, int device);
 void svnicp_destroy(svnicp_handle h);

@@ -33,7 +33,11 @@ int main(int argc, char **argv) {
   config.lr = scal[0];
   config.max_dist = scal[1];
   // the node holds the base-class pointer (OdometryPipeline.h:125)
-  std::unique_ptr<svnicp::SVGDICP> icp = std::make_unique<svnicp::SVNICP>(config, init, svnicp::ParticleWeightOpt{});
+  // ... and picks the class from the `class_type` parameter (OdometryPipeline.cpp:282-288)
+  const bool svgd = argc > 3 && std::string(argv[3]) == "SVGDICP";
+  std::unique_ptr<svnicp::SVGDICP> icp;
+  if (svgd) icp = std::make_unique<svnicp::SVGDICP>(config, init);
+  else icp = std::make_unique<svnicp::SVNICP>(config, init, svnicp::ParticleWeightOpt{});
   icp->add_cloud({src.data(), n_s, false}, {tgt.data(), n_t, false}, init);
   svnicp::InitialMean guess;
   for (int i = 0; i < 9; i++) guess.R[i] = R0[i];

@@ -34,22 +34,26 @@ def test_mirror_compiles_and_links(tmp_path):
 
 
 @pytest.mark.gpu
-def test_mirror_matches_python_mirror(tmp_path):
+@pytest.mark.parametrize("cls", ["SVNICP", "SVGDICP"])
+def test_mirror_matches_python_mirror(tmp_path, cls):
     exe = build_mirror(str(tmp_path))
     P, I, K = 48, 7, 40
     pb = synth.make_uniform_problem(P, 900, 9000, seed=4)
     prob, res = os.path.join(tmp_path, "problem.bin"), os.path.join(tmp_path, "result.bin")
     with open(prob, "wb") as f:
         f.write(struct.pack("6q", len(pb.source), len(pb.target), P, I, K, 1))
-        f.write(struct.pack("2d", 1.0, 3.0))
+        f.write(struct.pack("2d", 1.0 if cls == "SVNICP" else 0.03, 3.0))
         for a in (pb.source, pb.target, pb.init_pose, pb.R0, pb.t0):
             f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
-    out = subprocess.run([exe, prob, res], capture_output=True, text=True)
+    out = subprocess.run([exe, prob, res, cls], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     raw = np.fromfile(res, dtype=np.uint8)
     d = np.frombuffer(raw[: 8 * (48 + 7 * P)].tobytes(), dtype=np.float64)
     hist = np.frombuffer(raw[8 * (48 + 7 * P):].tobytes(), dtype=np.float32).reshape(I, 6 * P)
-    icp = sv.SVNICP(sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=3.0, lr=1.0, SVN_full_grad=True), pb.init_pose)
+    if cls == "SVNICP":
+        icp = sv.SVNICP(sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=3.0, lr=1.0, SVN_full_grad=True), pb.init_pose)
+    else:
+        icp = sv.SVGDICP(sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=3.0, lr=0.03, SVN_full_grad=True), pb.init_pose)
     icp.add_cloud(pb.source, pb.target, pb.init_pose)
     icp.set_initial_mean(pb.R0, pb.t0)
     icp.stein_align()
