@@ -160,6 +160,33 @@ int svnicp_get_tail_stamps(svnicp_handle h, double out10[10]);
 /* number of kernel launches issued by the last svnicp_align */
 int svnicp_get_launch_count(svnicp_handle h, int64_t *out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-resident local map: svnicp::VoxelHashMap (svn-icp/include/core/VoxelHashMap.h:28-72,
+ * src/core/VoxelHashMap.cpp:22-101) kept in HBM, so the target cloud of svnicp_add_cloud
+ * (target_on_device = 1) never crosses PCIe (the reference rebuilds and re-uploads it every scan,
+ * OdometryPipeline.cpp:577-581, :630).  Same status codes; no CPU fallback.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct svnicp_map_t *svnicp_map;
+/* VoxelHashMap(voxel_size, max_range, max_pointscount) (VoxelHashMap.h:40-43); capacity_voxels bounds the
+ * number of live voxels (the table holds 2x that many slots); max_pointscount <= 32. */
+int svnicp_map_create(svnicp_map *out, double voxel_size, double max_range, int max_pointscount, int64_t capacity_voxels, int device);
+void svnicp_map_destroy(svnicp_map m);
+const char *svnicp_map_last_error(svnicp_map m);
+/* Clear() (VoxelHashMap.h:54) */
+int svnicp_map_clear(svnicp_map m);
+/* AddPointCloud(new_cloud, new_pose) (VoxelHashMap.cpp:22-43) including RemoveFarPointCloud(new_pose.translation())
+ * (:93-101).  xyz: [n][3] sensor-frame points, float (dtype_f64 = 0, pcl::PointXYZ) or double; host or device.
+ * R row-major 3x3, t[3] = new_pose.  A voxel keeps its first max_pointscount points in cloud order. */
+int svnicp_map_add_cloud(svnicp_map m, const void *xyz, int64_t n, int dtype_f64, int on_device, const double R[9], const double t[3]);
+/* GetMap() (position = NULL, VoxelHashMap.cpp:45-51) / GetMap(pose, max_range) (:53-63; position = pose.translation()).
+ * *device_xyz: device pointer to [*n][3] doubles owned by the map, valid until the next call on it -- pass it to
+ * svnicp_add_cloud with target_on_device = 1.  Point order is arbitrary (as the reference's hash-map iteration). */
+int svnicp_map_get(svnicp_map m, const double position[3], double max_range, const double **device_xyz, int64_t *n);
+/* copy the first n points of the last svnicp_map_get result to the host (tests / visualisation) */
+int svnicp_map_download(svnicp_map m, double *out_xyz, int64_t n);
+/* Size() / Empty() (VoxelHashMap.h:55-56): live voxels and stored points */
+int svnicp_map_size(svnicp_map m, int64_t *voxels, int64_t *points);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,7 +44,7 @@ def _ptr(a):
 
 def build(force: bool = False) -> str:
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("svn_oracle.c", "svgd_oracle.c")]
+    srcs = [os.path.join(HERE, f) for f in ("svn_oracle.c", "svgd_oracle.c", "voxelmap_oracle.c")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -269,6 +269,74 @@ def make_svgd_params(iterations=30, lr=0.03, max_dist=3.0, check_early_stop=Fals
 class SvgdDumps(C.Structure):
     _fields_ = [("grad", C.c_void_p), ("stein", C.c_void_p), ("bandwidth", C.c_void_p), ("x_after", C.c_void_p),
                 ("corr_idx", C.c_void_p), ("corr_mask", C.c_void_p)]
+
+
+class VoxelMapOracle:
+    """Sequential restatement of svnicp::VoxelHashMap (voxelmap_oracle.c)."""
+
+    def __init__(self, voxel_size=1.0, max_range=80.0, max_pointscount=20):
+        self.lib = C.CDLL(build())
+        self.lib.oracle_vmap_create.restype = C.c_void_p
+        self.lib.oracle_vmap_get.restype = C.c_int64
+        self.lib.oracle_vmap_size.restype = C.c_int64
+        self.m = C.c_void_p(self.lib.oracle_vmap_create(C.c_double(voxel_size), C.c_double(max_range), C.c_int(max_pointscount)))
+
+    def __del__(self):
+        try:
+            self.lib.oracle_vmap_destroy(self.m)
+        except Exception:
+            pass
+
+    def AddPointCloud(self, cloud, R, t):
+        a = np.asarray(cloud)
+        f64 = a.dtype != np.float32
+        a = np.ascontiguousarray(a, dtype=np.float64 if f64 else np.float32)
+        self.lib.oracle_vmap_add(self.m, _ptr(a), C.c_int64(len(a)), C.c_int(int(f64)), _ptr(_f64(R).reshape(9)), _ptr(_f64(t).reshape(3)))
+
+    def GetMap(self, position=None, max_range=0.0):
+        pos = _ptr(_f64(position).reshape(3)) if position is not None else None
+        n = self.lib.oracle_vmap_get(self.m, pos, C.c_double(max_range), None)
+        out = np.zeros((n, 3))
+        self.lib.oracle_vmap_get(self.m, pos, C.c_double(max_range), _ptr(out))
+        return out
+
+    def Size(self):
+        return self.lib.oracle_vmap_size(self.m)
+
+    def Clear(self):
+        self.lib.oracle_vmap_clear(self.m)
+
+
+class ReferenceMap:
+    """The reference's own svnicp::VoxelHashMap (oracle/_ref/libvmap_ref.so: VoxelHashMap.cpp compiled unmodified over
+    stand-in PCL / Eigen / tsl types).  float32 clouds only (pcl::PointXYZI)."""
+
+    def __init__(self, voxel_size=1.0, max_range=80.0, max_pointscount=20):
+        self.lib = C.CDLL(os.path.join(HERE, "_ref", "libvmap_ref.so"))
+        self.lib.ref_vmap_create.restype = C.c_void_p
+        self.lib.ref_vmap_get.restype = C.c_int64
+        self.lib.ref_vmap_size.restype = C.c_int64
+        self.m = C.c_void_p(self.lib.ref_vmap_create(C.c_double(voxel_size), C.c_double(max_range), C.c_int(max_pointscount)))
+
+    def __del__(self):
+        try:
+            self.lib.ref_vmap_destroy(self.m)
+        except Exception:
+            pass
+
+    def AddPointCloud(self, cloud, R, t):
+        a = np.ascontiguousarray(cloud, dtype=np.float32)
+        self.lib.ref_vmap_add(self.m, _ptr(a), C.c_int64(len(a)), _ptr(_f64(R).reshape(9)), _ptr(_f64(t).reshape(3)))
+
+    def GetMap(self, position=None, max_range=0.0):
+        pos = _ptr(_f64(position).reshape(3)) if position is not None else None
+        n = self.lib.ref_vmap_get(self.m, pos, C.c_double(max_range), None)
+        out = np.zeros((n, 3))
+        self.lib.ref_vmap_get(self.m, pos, C.c_double(max_range), _ptr(out))
+        return out
+
+    def Size(self):
+        return self.lib.ref_vmap_size(self.m)
 
 
 def ref_available() -> bool:

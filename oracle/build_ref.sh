@@ -24,3 +24,7 @@ wait
 g++ -shared -o "$OUT/libsvnicp_ref.so" "$OUT/SVGDICP.o" "$OUT/SVNICP.o" "$OUT/ref_driver.o" \
     -L "$TORCH/lib" -Wl,-rpath,"$TORCH/lib" -ltorch -ltorch_cpu -lc10
 echo "built $OUT/libsvnicp_ref.so"
+# the reference's local map (VoxelHashMap.cpp, unmodified) over the stand-in PCL / Eigen / tsl / gtsam types of ref_shim_map
+g++ -O2 -std=c++17 -fPIC -w -I "$HERE/ref_shim_map" -I "$REF/include" -shared -o "$OUT/libvmap_ref.so" \
+    "$REF/src/core/VoxelHashMap.cpp" "$HERE/ref_driver_map.cpp"
+echo "built $OUT/libvmap_ref.so"

@@ -74,6 +74,8 @@ EXPORTS = [
     "svnicp_get_source_f32", "svnicp_get_correspondences", "svnicp_get_gn_system", "svnicp_get_stein", "svnicp_get_prune_stats",
     "svnicp_get_timing", "svnicp_get_slice", "svnicp_get_launch_count", "svnicp_set_profiling", "svnicp_get_phase_times",
     "svnicp_get_scan_info", "svnicp_get_tail_stamps",
+    "svnicp_map_create", "svnicp_map_destroy", "svnicp_map_last_error", "svnicp_map_clear", "svnicp_map_add_cloud", "svnicp_map_get",
+    "svnicp_map_download", "svnicp_map_size",
 ]
 
 
@@ -89,10 +91,14 @@ def load_library() -> C.CDLL:
         lib.svnicp_last_error.argtypes = [C.c_void_p]
         for name in EXPORTS:
             fn = getattr(lib, name)
-            if name not in ("svnicp_last_error", "svnicp_destroy", "svnicp_default_params"):
+            if name not in ("svnicp_last_error", "svnicp_destroy", "svnicp_default_params", "svnicp_map_last_error", "svnicp_map_destroy"):
                 fn.restype = C.c_int
         lib.svnicp_destroy.restype = None
         lib.svnicp_destroy.argtypes = [C.c_void_p]
+        lib.svnicp_map_destroy.restype = None
+        lib.svnicp_map_destroy.argtypes = [C.c_void_p]
+        lib.svnicp_map_last_error.restype = C.c_char_p
+        lib.svnicp_map_last_error.argtypes = [C.c_void_p]
         lib.svnicp_default_params.restype = None
         _lib = lib
     return _lib
@@ -359,3 +365,79 @@ class SVGDICP(SVNICP):
 
     def __init__(self, param: SteinICPParam, init_pose, device: int = -1):
         super().__init__(param, init_pose, None, device)
+
+
+class VoxelHashMap:
+    """Drop-in for svnicp::VoxelHashMap (VoxelHashMap.h:28-72, VoxelHashMap.cpp:22-101), device resident: the local map the
+    node keeps between scans (OdometryPipeline.cpp:577-581, :630).  Same method names; poses are (R [3,3], t [3])."""
+
+    def __init__(self, voxel_size: float = 1.0, max_range: float = 80.0, max_pointscount: int = 20, capacity_voxels: int = 1 << 19,
+                 device: int = -1):
+        self._lib = load_library()
+        self._m = C.c_void_p()
+        self.voxel_size_, self.max_range_, self.max_pointscount_ = voxel_size, max_range, max_pointscount
+        rc = self._lib.svnicp_map_create(C.byref(self._m), C.c_double(voxel_size), C.c_double(max_range), C.c_int(max_pointscount),
+                                         C.c_int64(capacity_voxels), C.c_int(device))
+        if rc != 0:
+            self._m = C.c_void_p()
+            raise SvnIcpError(f"svnicp_map_create failed ({rc}): " + (self._lib.svnicp_map_last_error(None) or b"").decode())
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise SvnIcpError(f"{what} failed ({rc}): " + (self._lib.svnicp_map_last_error(self._m) or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_m", None) and self._m.value:
+            self._lib.svnicp_map_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def Clear(self):
+        self._check(self._lib.svnicp_map_clear(self._m), "Clear")
+
+    def Size(self) -> int:
+        v = C.c_int64(0)
+        self._check(self._lib.svnicp_map_size(self._m, C.byref(v), None), "Size")
+        return v.value
+
+    def PointCount(self) -> int:
+        v = C.c_int64(0)
+        self._check(self._lib.svnicp_map_size(self._m, None, C.byref(v)), "Size")
+        return v.value
+
+    def Empty(self) -> bool:
+        return self.Size() == 0
+
+    def AddPointCloud(self, new_cloud, R, t):
+        """VoxelHashMap::AddPointCloud (VoxelHashMap.cpp:22-43).  new_cloud: [N,3] float32 (pcl::PointXYZ) or float64, host."""
+        a = np.asarray(new_cloud)
+        f64 = a.dtype != np.float32
+        a = np.ascontiguousarray(a, dtype=np.float64 if f64 else np.float32)
+        self._check(self._lib.svnicp_map_add_cloud(self._m, _p(a), C.c_int64(len(a)), C.c_int(int(f64)), C.c_int(0),
+                                                   _p(_f64(R).reshape(9)), _p(_f64(t).reshape(3))), "AddPointCloud")
+
+    def AddPointCloudDevice(self, ptr: int, n: int, f64: bool, R, t):
+        self._check(self._lib.svnicp_map_add_cloud(self._m, C.c_void_p(ptr), C.c_int64(n), C.c_int(int(f64)), C.c_int(1),
+                                                   _p(_f64(R).reshape(9)), _p(_f64(t).reshape(3))), "AddPointCloud")
+
+    def GetMapDevice(self, position=None, max_range: float = 0.0):
+        """GetMap() / GetMap(pose, max_range) (VoxelHashMap.cpp:45-63) -> (device pointer to [n,3] float64, n): feed it to
+        SVNICP.add_cloud_device as the target."""
+        ptr = C.c_void_p()
+        n = C.c_int64(0)
+        pos = _p(_f64(position).reshape(3)) if position is not None else None
+        self._check(self._lib.svnicp_map_get(self._m, pos, C.c_double(max_range), C.byref(ptr), C.byref(n)), "GetMap")
+        return ptr.value, n.value
+
+    def GetMap(self, position=None, max_range: float = 0.0) -> np.ndarray:
+        """Same, copied to the host: [n,3] float64 (values are float32-representable, like pcl::PointXYZ)."""
+        _, n = self.GetMapDevice(position, max_range)
+        out = np.zeros((n, 3))
+        self._check(self._lib.svnicp_map_download(self._m, _p(out), C.c_int64(n)), "GetMap")
+        return out
