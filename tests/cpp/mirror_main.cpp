@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "svnicp/SVNICP.hpp"
+#include "svnicp/VoxelHashMap.hpp"
 
 template <class T>
 static std::vector<T> rd(FILE *f, size_t n) {
@@ -38,10 +39,22 @@ int main(int argc, char **argv) {
   std::unique_ptr<svnicp::SVGDICP> icp;
   if (svgd) icp = std::make_unique<svnicp::SVGDICP>(config, init);
   else icp = std::make_unique<svnicp::SVNICP>(config, init, svnicp::ParticleWeightOpt{});
-  icp->add_cloud({src.data(), n_s, false}, {tgt.data(), n_t, false}, init);
   svnicp::InitialMean guess;
   for (int i = 0; i < 9; i++) guess.R[i] = R0[i];
   for (int i = 0; i < 3; i++) guess.t[i] = t0[i];
+  const bool via_map = argc > 4 && std::string(argv[4]) == "MAP";
+  std::unique_ptr<svnicp::VoxelHashMap> local_map;
+  if (via_map) {
+    // the node's flow (OdometryPipeline.cpp:576-581, :630): the map is fed world-frame points at the identity pose and
+    // hands the target back as a DEVICE cloud.  cap 32 / huge range: keeps every map point of this small problem
+    local_map = std::make_unique<svnicp::VoxelHashMap>(1.0, 1e6, 32, 1 << 16);
+    std::vector<float> tf(tgt.begin(), tgt.end());
+    local_map->AddPointCloud(tf, svnicp::InitialMean{});
+    const svnicp::CloudView target = local_map->GetMap(guess, 1e5);
+    icp->add_cloud({src.data(), n_s, false}, target, init);
+  } else {
+    icp->add_cloud({src.data(), n_s, false}, {tgt.data(), n_t, false}, init);
+  }
   icp->set_initial_mean(guess);
   if (icp->stein_align() != svnicp::ALIGN_SUCCESS) return 3;
   const auto mean = icp->get_transformation();

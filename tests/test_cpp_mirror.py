@@ -63,3 +63,31 @@ def test_mirror_matches_python_mirror(tmp_path, cls):
     np.testing.assert_array_equal(d[48:48 + 6 * P], icp.get_particles())
     np.testing.assert_array_equal(d[48 + 6 * P:], icp.get_particle_weight())
     np.testing.assert_array_equal(hist, icp.get_particle_history())
+
+
+@pytest.mark.gpu
+def test_mirror_local_map_feeds_registration(tmp_path):
+    """svnicp::VoxelHashMap (C++ mirror) -> GetMap(pose, range) device cloud -> add_cloud, as the node does."""
+    exe = build_mirror(str(tmp_path))
+    P, I, K = 32, 5, 24
+    pb = synth.make_uniform_problem(P, 600, 6000, seed=9)
+    prob, res = os.path.join(tmp_path, "problem.bin"), os.path.join(tmp_path, "result.bin")
+    with open(prob, "wb") as f:
+        f.write(struct.pack("6q", len(pb.source), len(pb.target), P, I, K, 1))
+        f.write(struct.pack("2d", 1.0, 3.0))
+        for a in (pb.source, pb.target, pb.init_pose, pb.R0, pb.t0):
+            f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    out = subprocess.run([exe, prob, res, "SVNICP", "MAP"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    d = np.fromfile(res, dtype=np.uint8)[: 8 * 48].view(np.float64)
+    # same thing through the Python mirror: the map stores float32 points, so the target is the float32-rounded cloud
+    m = sv.VoxelHashMap(1.0, 1e6, 32, capacity_voxels=1 << 16)
+    m.AddPointCloud(pb.target.astype(np.float32), np.eye(3), np.zeros(3))
+    tgt = m.GetMap(pb.t0, 1e5)
+    assert len(tgt) == len(pb.target)  # cap 32 was enough for every voxel of this problem
+    icp = sv.SVNICP(sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=3.0, lr=1.0, SVN_full_grad=True), pb.init_pose)
+    icp.add_cloud(pb.source, tgt, pb.init_pose)
+    icp.set_initial_mean(pb.R0, pb.t0)
+    icp.stein_align()
+    # point ORDER of the two map instances may differ (hash slots); it only matters for exact distance ties
+    np.testing.assert_allclose(d[:6], icp.get_transformation(), atol=1e-12, rtol=0)
