@@ -33,6 +33,17 @@ def test_mirror_compiles_and_links(tmp_path):
     assert subprocess.call([os.path.join(tmp_path, "abi")]) == 0
 
 
+def test_stein_msgs_producer_mapping(tmp_path):
+    """stein_msgs field mapping (svnicp/stein_msgs_compat.hpp): [6][P] slices -> x,y,z,roll,pitch,yaw, as
+    OdometryPipeline.cpp:942-987 does.  Pure host code: runs without a GPU."""
+    from svn_icp_b200 import build
+    lib = build.build()
+    exe = os.path.join(tmp_path, "msgs_main")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "svn_icp_b200", "include"),
+                           os.path.join(ROOT, "tests", "cpp", "msgs_main.cpp"), "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)])
+    assert subprocess.call([exe]) == 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cls", ["SVNICP", "SVGDICP"])
 def test_mirror_matches_python_mirror(tmp_path, cls):
