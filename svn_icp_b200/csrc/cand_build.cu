@@ -22,8 +22,13 @@ namespace svn {
 constexpr unsigned long long EMPTY_KEY = 0xffffffffffffffffull;
 constexpr int RING_MAX = 6;
 constexpr int KNN_WARPS = 4;
-constexpr int KNN_CAP = 1024;  // (d^2, pos, idx) entries per warp, power of two (bitonic sort).  Measured at configs[1]:
-                               // 512 (24 warps/SM) -> 6.2 ms because of mid-search compactions, 1024 (12 warps/SM) -> 3.9 ms
+#ifndef SVN_KNN_CAP
+#define SVN_KNN_CAP 512
+#endif
+// (d^2, pos, idx) entries per warp, power of two (bitonic sort).  The kernel is latency bound, so resident warps matter:
+// 1024 entries = 16 KB per warp -> 12 warps/SM; 512 -> 24 warps/SM, with buffer overflows relieved by a histogram cut
+// (warp_cut) instead of a full sort (measured at configs[1]: see DESIGN.md section 4).
+constexpr int KNN_CAP = SVN_KNN_CAP;
 constexpr int KNN_BINS = 64;
 
 struct Ent {
@@ -143,6 +148,61 @@ __device__ int warp_compact(Ent *buf, int count, int K, double *tau) {
   return c;
 }
 
+// Cheap overflow relief (no sort): 64-bin histogram of d over [0, max d in the buffer]; keep every entry up to the bin
+// that holds the K-th smallest -- an exact superset of the K nearest seen so far.  The bin function is monotone in d, so
+// a later point may be dropped iff its bin exceeds *cut_bin under the same *cut_scale.  Returns the new count (unchanged
+// when the cut cannot shrink the buffer: all keys in one bin).
+__device__ __forceinline__ int cut_bin_of(double d, double scale) { return min(KNN_BINS - 1, (int)(d * scale)); }
+
+__device__ int warp_cut(Ent *buf, int count, int K, double *cut_scale, int *cut_bin, int *hist) {
+  const int lane = lane_id();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  double dmax = 0.0;
+  for (int i = lane; i < count; i += 32) dmax = fmax(dmax, buf[i].d);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  if (!(dmax > 0.0) || dmax == INFINITY) return count;
+  const double scale = (double)KNN_BINS / dmax;
+  hist[lane] = 0;
+  hist[lane + 32] = 0;
+  __syncwarp();
+  for (int i = lane; i < count; i += 32) atomicAdd(&hist[cut_bin_of(buf[i].d, scale)], 1);
+  __syncwarp();
+  const int h0 = hist[2 * lane], h1 = hist[2 * lane + 1];
+  int incl = h0 + h1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int before = incl - h0 - h1;
+  int tbin = KNN_BINS;
+  if (before < K && before + h0 >= K) tbin = 2 * lane;
+  else if (before + h0 < K && incl >= K) tbin = 2 * lane + 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tbin = min(tbin, __shfl_xor_sync(0xffffffffu, tbin, o));
+  __syncwarp();
+  if (tbin >= KNN_BINS - 1) return count;  // fewer than K entries, or the K-th sits in the last bin: nothing to drop
+  int m_out = 0;
+  for (int i0 = 0; i0 < count; i0 += 32) {
+    const int i = i0 + lane;
+    Ent e;
+    bool keep = false;
+    if (i < count) {
+      e = buf[i];
+      keep = cut_bin_of(e.d, scale) <= tbin;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) buf[m_out + __popc(m & lt_mask)] = e;
+    m_out += __popc(m);
+    __syncwarp();
+  }
+  *cut_scale = scale;
+  *cut_bin = tbin;
+  return m_out;
+}
+
 __device__ __forceinline__ double dist2(const double q[3], const double *__restrict__ m) {
   const double dx = q[0] - m[0], dy = q[1] - m[1], dz = q[2] - m[2];
   return fma(dz, dz, fma(dy, dy, dx * dx));  // knn.cu:101-106 after nvcc's fma contraction
@@ -165,7 +225,15 @@ k_knn(const double *__restrict__ q0, int row_lo, int row_hi, const double *__res
     const int c0[3] = {cell_of(q[0], inv_cell), cell_of(q[1], inv_cell), cell_of(q[2], inv_cell)};
     int count = 0;
     double tau = INFINITY, rs2_done = 0.0;
+    double cut_scale = 0.0;       // histogram cut in force (warp_cut): drop d when cut_bin_of(d, cut_scale) > cut_bin
+    int cut_bin = KNN_BINS;
     bool done = false;
+    // overflow: first the cheap histogram cut, the full sort only if that could not make room
+#define SVN_KNN_RELIEVE()                                                                         \
+  if (count + 32 > KNN_CAP) {                                                                     \
+    count = warp_cut(buf, count, K, &cut_scale, &cut_bin, s_hist[warp]);                          \
+    if (count + 32 > KNN_CAP) count = warp_compact(buf, count, K, &tau);                          \
+  }
 
     for (int r = 0; r <= RING_MAX && !done; r++) {
       const int side = 2 * r + 1, ncube = side * side * side;
@@ -205,13 +273,13 @@ k_knn(const double *__restrict__ q0, int row_lo, int row_hi, const double *__res
             e.d = dist2(q, sxyz + 3 * (size_t)pos);
             e.pos = pos;
             e.idx = sidx[pos];
-            keep = e.d <= tau;
+            keep = e.d <= tau && (cut_bin >= KNN_BINS || cut_bin_of(e.d, cut_scale) <= cut_bin);
           }
           const unsigned m = __ballot_sync(0xffffffffu, keep);
           if (keep) buf[count + __popc(m & lt_mask)] = e;
           count += __popc(m);
           __syncwarp();
-          if (count + 32 > KNN_CAP) count = warp_compact(buf, count, K, &tau);
+          SVN_KNN_RELIEVE()
         }
         __syncwarp();
       }
@@ -235,6 +303,7 @@ k_knn(const double *__restrict__ q0, int row_lo, int row_hi, const double *__res
       if (lane == 0) atomicAdd(fallback_count, 1);
       count = 0;
       tau = INFINITY;
+      cut_bin = KNN_BINS;
       for (int t0 = 0; t0 < n_t; t0 += 32) {
         const int t = t0 + lane;
         bool keep = false;
@@ -243,15 +312,16 @@ k_knn(const double *__restrict__ q0, int row_lo, int row_hi, const double *__res
           e.d = dist2(q, sxyz + 3 * (size_t)t);
           e.pos = t;
           e.idx = sidx[t];
-          keep = e.d <= tau;
+          keep = e.d <= tau && (cut_bin >= KNN_BINS || cut_bin_of(e.d, cut_scale) <= cut_bin);
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (keep) buf[count + __popc(m & lt_mask)] = e;
         count += __popc(m);
         __syncwarp();
-        if (count + 32 > KNN_CAP) count = warp_compact(buf, count, K, &tau);
+        SVN_KNN_RELIEVE()
       }
     }
+#undef SVN_KNN_RELIEVE
     if (done) {
       // >= K points lie inside rs2_done.  Cut the buffer down before sorting: 64-bin histogram of d over [0, rs2),
       // keep everything up to the bin in which the K-th smallest falls (exact superset of the K nearest).
@@ -329,11 +399,8 @@ int launch_cand_build(const CandBuildArgs &a, cudaStream_t st) {
   k_grid_count<<<cdiv(a.n_t, T), T, 0, st>>>(a.tgt64, a.n_t, 1.0 / a.cell, a.keys, a.counts, a.pt_slot, (unsigned)(a.table_size - 1)); launches++;
   k_grid_alloc<<<cdiv(a.table_size, T), T, 0, st>>>(a.counts, a.starts, a.table_size, a.cursor); launches++;
   k_grid_scatter<<<cdiv(a.n_t, T), T, 0, st>>>(a.tgt64, a.n_t, a.pt_slot, a.starts, a.fill, a.sxyz, a.sidx); launches++;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes());
-    attr_set = true;
-  }
+  // per scan, not once per process: the attribute is per device, and a process may hold handles on several devices
+  if (knn_smem_bytes() > 48 * 1024) cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes());
   int grid = cdiv(a.row_hi - a.row_lo, KNN_WARPS);
   const int max_grid = a.sm_count * 12;
   if (grid > max_grid) grid = max_grid;

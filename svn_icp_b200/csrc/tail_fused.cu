@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
   const int gtid = blockIdx.x * blockDim.x + tid, gn = gridDim.x * blockDim.x;
   const int P = a.P;
   const int it = c->iter;
+  // previous iteration's median (bandwidth is rewritten only after the barriers below): the guess of the fast median path
+  const double med_guess = c->bandwidth * log((double)(P + 1));
   TF_STAMP(0);
 
   // ------------------------------------------------------------------ decide (as k_decide, redundantly per CTA)
@@ -147,7 +149,96 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
       X = sx;
     }
     unsigned long long prefix = 0ull, rank = ((unsigned long long)P * (unsigned long long)P - 1ull) / 2ull;
-    for (int s = 0; s < MED_PASSES; s++) {
+    bool have_median = false;
+    double median = 0.0;
+    // ---- fast path (2 passes instead of 5): the median moves little between iterations, so histogram LINEARLY around the
+    // previous one (8190 bins over [0.5, 1.5) x previous median, one bin below, one above), then gather the few dozen
+    // values of the bin that holds the rank and pick the exact order statistic.  Same value as the radix select (the
+    // lower median is unique), so the bandwidth is bit-identical to the 5-pass path; any miss (median left the window,
+    // degenerate bin) falls back to it.  Every branch below depends only on data all CTAs see identically.
+    constexpr int TF_COLLECT_CAP = 4096;  // doubles; staged in s_raw (32 KB)
+    if (P >= 64 && it > 0 && med_guess > 0.0 && med_guess < INFINITY) {
+      const double lo = 0.5 * med_guess, hi = 1.5 * med_guess, scale = (double)(MED_BINS - 2) / (hi - lo);
+      auto bin_of = [&](double d) -> unsigned {  // monotone non-decreasing in d; NaN sorts last like its bit pattern
+        if (d < lo) return 0u;
+        if (!(d < hi)) return (unsigned)(MED_BINS - 1);
+        const int b = (int)((d - lo) * scale);
+        return 1u + (unsigned)min(b, MED_BINS - 3);
+      };
+      for (int i = tid; i < MED_BINS; i += blockDim.x) s_hist[i] = 0u;
+      __syncthreads();
+      for (int i = blockIdx.x; i < P; i += gridDim.x)
+        for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
+          const int j = j0 + tid;
+          unsigned bin = 0;
+          if (j < P) {
+            double d2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+              const double df = X[d * P + i] - X[d * P + j];
+              d2 += df * df;
+            }
+            bin = bin_of(d2);
+          }
+          const unsigned mm = __ballot_sync(0xffffffffu, j < P);
+          if (j < P) {
+            const unsigned peers = __match_any_sync(mm, bin);
+            if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));
+          }
+        }
+      if (blockIdx.x == 0 && tid == 0) atomicAdd(&s_hist[0], (unsigned)P);  // the diagonal: exact zeros, below lo
+      __syncthreads();
+      for (int i = tid; i < MED_BINS; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&a.hist[i], s_hist[i]);
+      grid.sync();
+      unsigned long long tbin = 0ull, trank = 0ull;
+      tf_select(a.hist, 0ull, rank, MED_BINS, 13, &tbin, &trank, s_warp, s_res);
+      if (tbin != 0ull && tbin != (unsigned long long)(MED_BINS - 1)) {
+        // gather the values of that bin once per unordered pair (each stands for two entries of the P x P matrix)
+        unsigned *cursor = a.hist + MED_BINS;                                   // zeroed with the histograms
+        double *list = reinterpret_cast<double *>(a.hist + 2 * MED_BINS);       // rows 2..4: 12288 doubles
+        for (int i = blockIdx.x; i < P; i += gridDim.x)
+          for (int j = i + 1 + tid; j < P; j += blockDim.x) {
+            double d2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+              const double df = X[d * P + i] - X[d * P + j];
+              d2 += df * df;
+            }
+            if (bin_of(d2) == (unsigned)tbin) {
+              const unsigned k = atomicAdd(cursor, 1u);
+              if (k < (unsigned)TF_COLLECT_CAP) list[k] = d2;
+            }
+          }
+        grid.sync();
+        const unsigned n_c = __ldcg(cursor);
+        if (n_c >= 1u && n_c <= (unsigned)TF_COLLECT_CAP) {
+          double *sl = reinterpret_cast<double *>(s_raw);
+          for (unsigned k = tid; k < n_c; k += blockDim.x) sl[k] = __ldcg(list + k);
+          if (tid == 0) s_flag[1] = 0;
+          __syncthreads();
+          const unsigned target = (unsigned)(trank >> 1);  // index among the distinct pairs of the bin, ascending
+          for (unsigned k = tid; k < n_c; k += blockDim.x) {
+            const double v = sl[k];
+            unsigned less = 0, eq = 0;
+            for (unsigned u = 0; u < n_c; u++) {
+              const double w = sl[u];
+              less += (w < v) ? 1u : 0u;
+              eq += (w == v) ? 1u : 0u;
+            }
+            if (less <= target && target < less + eq) { s_res[0] = (unsigned long long)__double_as_longlong(v); s_flag[1] = 1; }
+          }
+          __syncthreads();
+          if (s_flag[1]) { have_median = true; median = __longlong_as_double((long long)s_res[0]); }
+          __syncthreads();
+        }
+      }
+      if (!have_median) {  // miss: clean the scratch the radix passes expect to be zero
+        for (int i = gtid; i < MED_PASSES * MED_BINS; i += gn) a.hist[i] = 0u;
+        grid.sync();
+      }
+    }
+    for (int s = 0; s < MED_PASSES && !have_median; s++) {
       const int nb = 1 << tf_pass_bits(s);
       for (int i = tid; i < nb; i += blockDim.x) s_hist[i] = 0u;
       __syncthreads();
@@ -187,7 +278,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
       grid.sync();
       tf_select(gh, prefix, rank, nb, tf_pass_bits(s), &prefix, &rank, s_warp, s_res);
     }
-    h = __longlong_as_double((long long)prefix) / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
+    if (!have_median) median = __longlong_as_double((long long)prefix);
+    h = median / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
     if (gtid == 0) c->bandwidth = h;
   }
 
