@@ -123,13 +123,18 @@ def cpu_baseline_port(pb):
     O = orc.Oracle()
     K, I = WORKLOAD["K"], WORKLOAD["iterations"]
 
-    def run(ns, iters):
+    def run_once(ns, iters):
         prm = orc.make_params(iterations=iters, knn_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], svn_full_grad=WORKLOAD["svn_full_grad"])
+        src = _subsample(pb, ns)
         t0 = time.time()
-        O.align(prm, _subsample(pb, ns), pb.target, pb.init_pose, pb.R0, pb.t0)
+        O.align(prm, src, pb.target, pb.init_pose, pb.R0, pb.t0)
         return time.time() - t0
 
-    t_scan, desc = _sampled_scan_time(run, len(pb.source), I, 256, 512)
+    def run(ns, iters):  # best of two: the four timings are differenced, so one-off stalls (thread-pool start, page faults) matter
+        return min(run_once(ns, iters), run_once(ns, iters))
+
+    run_once(256, 1)  # warm-up: OpenMP thread pool, page-in of the map
+    t_scan, desc = _sampled_scan_time(run, len(pb.source), I, 1024, 2048)
     return dict(value=1.0 / t_scan, unit="scans/sec", cores=O.num_threads(), kind="port",
                 sample=f"C port (OpenMP): all {pb.init_pose.shape[1]} particles, full {len(pb.target)}-point map; " + desc)
 

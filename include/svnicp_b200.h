@@ -132,7 +132,8 @@ int svnicp_initialize_particles_gaussian(int particle_count, const double cov_di
 
 /* ---- parity / debug taps (no reference counterpart; used by tests and bench only) ---- */
 int svnicp_iterations_done(svnicp_handle h, int32_t *out);
-/* candidate table of the last scan: global map indices [n_s][K], ascending (d0^2, index). */
+/* candidate table of the last scan: global map indices [n_s][K], ascending (d0^2, index).  On a sharded handle the
+ * index table is only all-gathered when the handle was created with debug_corr (out_idx then errors otherwise). */
 int svnicp_get_candidates(svnicp_handle h, int32_t *out_idx /*[n_s][K]*/, float *out_rel_xyz /*[n_s][K][3] or NULL*/);
 /* fp32 source as the kernels see it: R0*s [n_s][3] */
 int svnicp_get_source_f32(svnicp_handle h, float *out_xyz);

@@ -571,7 +571,8 @@ int svnicp_align(svnicp_handle h) {
     // table equals the single-GPU table bit for bit); in place, this rank's block already sits at its offset
     const size_t blk = (size_t)h->rows_per_rank * h->K;
     NC(g_nccl.AllGather(h->cand.p + (size_t)h->rank * blk, h->cand.p, blk * 4, ncclFloat, h->comm, st));
-    NC(g_nccl.AllGather(h->cand_idx.p + (size_t)h->rank * blk, h->cand_idx.p, blk, ncclInt32, h->comm, st));
+    // the global map indices only feed the parity taps (svnicp_get_candidates / _get_correspondences): 20 % of the volume
+    if (h->prm.debug_corr) NC(g_nccl.AllGather(h->cand_idx.p + (size_t)h->rank * blk, h->cand_idx.p, blk, ncclInt32, h->comm, st));
   }
   if (h->pair_mode) h->launches += launch_spair(h->sp.p, h->spair.p, h->n_pad, st);
   CU(cudaGetLastError());
@@ -795,6 +796,8 @@ int svnicp_iterations_done(svnicp_handle h, int32_t *out) {
 
 int svnicp_get_candidates(svnicp_handle h, int32_t *out_idx, float *out_rel) {
   if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
+  if (out_idx && h->n_ranks > 1 && !h->prm.debug_corr)
+    return fail(h, SVNICP_ERR_INVALID, "sharded handle created without debug_corr: the map-index table was not gathered");
   CU(cudaSetDevice(h->device));
   const size_t n = (size_t)h->n_s * h->K;
   if (out_idx) CU(cudaMemcpy(out_idx, h->cand_idx.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));

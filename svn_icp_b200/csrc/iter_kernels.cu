@@ -457,27 +457,10 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_finalize(IterArgs a) {
   if (a.ctrl->stop) return;
-  const int lane = lane_id();
-  const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (l >= a.P_l) return;
-  const int nrows = a.n_slices * a.RG;
-  // fixed order: lane j (+16) sums the even (odd) partial rows of sum j with 4 independent chains, then odd joins even
-  const int j16 = lane & 15, half = lane >> 4;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int r = half;
-  for (; r + 6 < nrows; r += 8) {
-    s0 += a.part[((size_t)r * a.P_l + l) * NACC + j16];
-    s1 += a.part[((size_t)(r + 2) * a.P_l + l) * NACC + j16];
-    s2 += a.part[((size_t)(r + 4) * a.P_l + l) * NACC + j16];
-    s3 += a.part[((size_t)(r + 6) * a.P_l + l) * NACC + j16];
-  }
-  for (; r < nrows; r += 2) s0 += a.part[((size_t)r * a.P_l + l) * NACC + j16];
-  double s = (s0 + s1) + (s2 + s3);
-  s += __shfl_down_sync(0xffffffffu, s, 16);
+  const int l = blockIdx.x;  // one CTA (FIN_WARPS warps) per local particle
   double v[NACC];
-#pragma unroll
-  for (int j = 0; j < NACC; j++) v[j] = __shfl_sync(0xffffffffu, s, j);
-  if (lane != 0) return;
+  gn_sum_partials(a, l, v);
+  if (threadIdx.x != 0) return;
   const int p = a.p_lo + l;
   const double *R0 = a.sc.R0;
   double Rp[9], Rt[9];
@@ -591,7 +574,7 @@ int launch_gn(const IterArgs &a, cudaStream_t st) {
 }
 
 int launch_finalize(const IterArgs &a, cudaStream_t st) {
-  k_finalize<<<cdiv((long long)a.P_l * 32, 128), 128, 0, st>>>(a);
+  if (a.P_l > 0) k_finalize<<<a.P_l, FIN_WARPS * 32, 0, st>>>(a);
   return 1;
 }
 

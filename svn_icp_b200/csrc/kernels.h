@@ -60,6 +60,40 @@ struct IterArgs {
   int32_t *dbg_idx;
   uint8_t *dbg_mask;
 };
+#ifdef __CUDACC__
+// Fixed-order fp64 sum of the Gauss-Newton partial rows of local particle l (k_finalize, k_finalize_first): one CTA of
+// FIN_WARPS warps per particle.  Lane (j = lane & 15, half = lane >> 4) of warp w sums partial rows half + 2 (w + FIN_WARPS k)
+// of sum j over four independent chains, the odd half joins the even one, then the warps are added in ascending order.
+// The order depends only on the number of partial rows, never on timing.  Result: v[0..NACC) valid in EVERY thread of the CTA.
+constexpr int FIN_WARPS = 4;
+__device__ __forceinline__ void gn_sum_partials(const IterArgs &a, int l, double v[NACC]) {
+  __shared__ double s_fin[FIN_WARPS][NACC];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nrows = a.n_slices * a.RG;
+  const int j16 = lane & 15, half = lane >> 4;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const int step = 2 * FIN_WARPS;
+  int r = half + 2 * w;
+  for (; r + 3 * step < nrows; r += 4 * step) {
+    s0 += a.part[((size_t)r * a.P_l + l) * NACC + j16];
+    s1 += a.part[((size_t)(r + step) * a.P_l + l) * NACC + j16];
+    s2 += a.part[((size_t)(r + 2 * step) * a.P_l + l) * NACC + j16];
+    s3 += a.part[((size_t)(r + 3 * step) * a.P_l + l) * NACC + j16];
+  }
+  for (; r < nrows; r += step) s0 += a.part[((size_t)r * a.P_l + l) * NACC + j16];
+  double s = (s0 + s1) + (s2 + s3);
+  s += __shfl_down_sync(0xffffffffu, s, 16);
+  if (lane < NACC) s_fin[w][lane] = s;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NACC; j++) {
+    double t = s_fin[0][j];
+#pragma unroll
+    for (int ww = 1; ww < FIN_WARPS; ww++) t += s_fin[ww][j];
+    v[j] = t;
+  }
+}
+#endif
 int launch_prep(const IterArgs &a, cudaStream_t st, int x_only);
 // packed fp32x2 "pair mode" (gn_pair.cu): two source points per thread step
 void init_pair_kernels();

@@ -50,26 +50,10 @@ __global__ void k_svgd_init(SvgdArgs s, const double *init_pose, double *R, doub
 //   rec.b = sgd_gradient * gradient_scaling_factor_   (:454)
 __global__ void __launch_bounds__(128) k_finalize_first(IterArgs a, SvgdArgs s) {
   if (a.ctrl->stop) return;
-  const int lane = lane_id();
-  const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (l >= a.P_l) return;
-  const int nrows = a.n_slices * a.RG;
-  const int j16 = lane & 15, half = lane >> 4;  // same fixed order as k_finalize
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int r = half;
-  for (; r + 6 < nrows; r += 8) {
-    s0 += a.part[((size_t)r * a.P_l + l) * NACC + j16];
-    s1 += a.part[((size_t)(r + 2) * a.P_l + l) * NACC + j16];
-    s2 += a.part[((size_t)(r + 4) * a.P_l + l) * NACC + j16];
-    s3 += a.part[((size_t)(r + 6) * a.P_l + l) * NACC + j16];
-  }
-  for (; r < nrows; r += 2) s0 += a.part[((size_t)r * a.P_l + l) * NACC + j16];
-  double sum = (s0 + s1) + (s2 + s3);
-  sum += __shfl_down_sync(0xffffffffu, sum, 16);
+  const int l = blockIdx.x;  // one CTA (FIN_WARPS warps) per local particle, same fixed order as k_finalize
   double v[NACC];
-#pragma unroll
-  for (int j = 0; j < NACC; j++) v[j] = __shfl_sync(0xffffffffu, sum, j);
-  if (lane != 0) return;
+  gn_sum_partials(a, l, v);
+  if (threadIdx.x != 0) return;
   const int p = a.p_lo + l;
   const double *R0 = a.sc.R0;
   const double *x = s.pose6 + (size_t)p * 6;
@@ -269,7 +253,7 @@ int launch_svgd_init(const SvgdArgs &s, const double *init_pose_dev, double *R, 
   return 1;
 }
 int launch_finalize_first(const IterArgs &a, const SvgdArgs &s, cudaStream_t st) {
-  k_finalize_first<<<cdiv((long long)a.P_l * 32, 128), 128, 0, st>>>(a, s);
+  if (a.P_l > 0) k_finalize_first<<<a.P_l, FIN_WARPS * 32, 0, st>>>(a, s);
   return 1;
 }
 int launch_svgd_rec(double *rec, const double *src6, const double *dnorm, int lo, int n, int dn_off, cudaStream_t st) {

@@ -466,7 +466,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
   double accc[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) accc[i] = 0.0;
-  for (int l = gtid; l < a.P_l; l += gn) {
+  // particle l -> CTA l % grid, thread l / grid: a long serial fp64 chain per particle (Exp, J_l, Log, two 3x3 products), so
+  // spread the particles over ALL SMs (7 threads on each of 148 SMs at P = 1000) instead of filling two CTAs
+  for (int l = blockIdx.x + gridDim.x * tid; l < a.P_l; l += gn) {
     const int p = a.p_lo + l;
     double d[6];
 #pragma unroll
