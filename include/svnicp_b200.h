@@ -144,7 +144,8 @@ int svnicp_get_correspondences(svnicp_handle h, float *out_transforms, int32_t *
 int svnicp_get_gn_system(svnicp_handle h, double *out_H, double *out_b, double *out_x);
 /* Stein step of the last executed iteration, local slice: delta [P_local][6]; bandwidth h. */
 int svnicp_get_stein(svnicp_handle h, double *out_delta, double *out_bandwidth);
-/* mean candidates per (point) kept by the exact pruning pass, per iteration [iterations] */
+/* mean candidates per (point) kept by the exact pruning pass, per iteration [iterations]
+ * (with SVNICP_DEBUG_REUSE set in the environment: the fraction of rows pruned from the previous iteration's list) */
 int svnicp_get_prune_stats(svnicp_handle h, double *out_mean_kept, int32_t *rows);
 /* device time of the phases of the last scan in ms: {setup, iterations, epilogue, total} */
 int svnicp_get_timing(svnicp_handle h, double out4[4]);

@@ -94,6 +94,10 @@ struct svnicp_handle_t {
   DevBuf<double> pose6, prev, opt_state;
   int optimizer = -1;
   DevBuf<float4> sp, cand, clist, spair;
+  // list reuse across iterations (k_filter): second list buffer, true list lengths and the balls the lists are exact for
+  DevBuf<float4> clist2, ball[2];
+  DevBuf<int> ccount2, cbase[2];
+  int filter_reuse = 1;
   int pair_mode = 0;
   int rows_per_rank = 0;
   DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc, cand_idx;
@@ -328,6 +332,8 @@ void svnicp_destroy(svnicp_handle h) {
   h->prep_scratch_i.release();
   for (auto *b : d) b->release();
   h->sp.release(); h->cand.release(); h->clist.release(); h->spair.release();
+  h->clist2.release(); h->ccount2.release();
+  for (int i = 0; i < 2; i++) { h->ball[i].release(); h->cbase[i].release(); }
   h->cand_idx.release();
   h->ccount.release(); h->counts.release(); h->starts.release(); h->fill.release(); h->pt_slot.release(); h->sidx.release(); h->misc.release();
   h->keys.release(); h->kept_hist.release(); h->xf.release(); h->dbg_xf.release(); h->history.release(); h->hist.release(); h->ctrl.release();
@@ -442,6 +448,17 @@ int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int sou
   CU(h->clist.ensure((size_t)n_pad * h->Kp));
   CU(h->ccount.ensure((size_t)n_pad + 64));
   CU(cudaMemsetAsync(h->ccount.p, 0, ((size_t)n_pad + 64) * sizeof(int), h->stream));
+  // SVNICP_FILTER_FULL=1: prune from the full K-slot table every iteration (A/B measurements, roofline of the streaming pass)
+  h->filter_reuse = (!h->pair_mode && getenv("SVNICP_FILTER_FULL") == nullptr) ? 1 : 0;
+  if (h->filter_reuse) {
+    CU(h->clist2.ensure((size_t)n_pad * h->Kp));
+    CU(h->ccount2.ensure((size_t)n_pad + 64));
+    CU(cudaMemsetAsync(h->ccount2.p, 0, ((size_t)n_pad + 64) * sizeof(int), h->stream));
+    for (int i = 0; i < 2; i++) {
+      CU(h->ball[i].ensure((size_t)n_pad + 64));
+      CU(h->cbase[i].ensure((size_t)n_pad + 64));
+    }
+  }
   size_t table = 1024;
   while (table < (size_t)2 * n_t) table <<= 1;
   CU(h->keys.ensure(table));
@@ -627,6 +644,17 @@ int svnicp_align(svnicp_handle h) {
     PROF(0);
     if (!fused_tail || e == 0) h->launches += launch_prep(ia, st, 0);  // the fused tail prepares the next iteration itself
     PROF(1);
+    if (h->filter_reuse) {  // ping-pong: iteration e prunes the lists of iteration e-1 wherever its ball still covers this one's
+      const int cur = e & 1;
+      ia.clist = cur ? h->clist2.p : h->clist.p;
+      ia.ccount = cur ? h->ccount2.p : h->ccount.p;
+      ia.cbase = h->cbase[cur].p;
+      ia.ball = h->ball[cur].p;
+      ia.clist_prev = e > 0 ? (cur ? h->clist.p : h->clist2.p) : nullptr;
+      ia.cbase_prev = h->cbase[cur ^ 1].p;
+      ia.ball_prev = h->ball[cur ^ 1].p;
+      ia.kept_hist = h->kept_hist.p;
+    }
     h->launches += h->pair_mode ? launch_filter_pair(ia, st) : launch_filter(ia, st);
     PROF(2);
     h->launches += h->pair_mode ? launch_gn_pair(ia, st) : launch_gn(ia, st);
@@ -861,7 +889,12 @@ int svnicp_get_prune_stats(svnicp_handle h, double *out_mean_kept, int32_t *rows
   const int I = h->prm.iterations;
   if (rows) *rows = I;
   if (out_mean_kept)
-    for (int i = 0; i < I; i++) out_mean_kept[i] = (double)h->h_kept[i] / (double)(h->n_s > 0 ? h->n_s : 1);
+    for (int i = 0; i < I; i++) {
+      const unsigned long long v = h->h_kept[i];
+      const double den = (double)(h->n_s > 0 ? h->n_s : 1);
+      // SVNICP_DEBUG_REUSE=1: fraction of rows pruned from the previous list instead of mean kept candidates (tuning aid)
+      out_mean_kept[i] = getenv("SVNICP_DEBUG_REUSE") ? (double)(v >> 40) / den : (double)(v & ((1ull << 40) - 1ull)) / den;
+    }
   return SVNICP_OK;
 }
 

@@ -175,9 +175,22 @@ __global__ void __launch_bounds__(1024) k_prep(IterArgs a, int x_only) {
 // ---------------------------------------------------------------------------------------------
 constexpr float PRUNE_MARGIN = 1e-4f;  // metres; absorbs every fp32 rounding in q, qbar and the norms
 
+// Which pruning kernel runs this iteration (both are launched, one returns at once; decided on the device because the
+// host runs ahead of the GPU): while the lists are long (mean kept > FR_SWITCH) streaming the K-slot table with a warp per
+// row is faster (52 us, HBM bound); once they are short, k_filter_reuse prunes the previous lists with a thread per row.
+constexpr int FR_SWITCH = 12;
+__device__ __forceinline__ bool filter_use_reuse(const IterArgs &a) {
+  if (!a.clist_prev || !a.kept_hist) return false;
+  const int it = a.ctrl->iter;
+  if (it < 1) return false;
+  const unsigned long long kept_prev = a.kept_hist[it - 1] & ((1ull << 40) - 1ull);
+  return kept_prev <= (unsigned long long)FR_SWITCH * (unsigned long long)a.n_s;
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
   if (a.ctrl->stop) return;
+  if (filter_use_reuse(a)) return;  // k_filter_reuse takes this iteration
   const int lane = lane_id();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const Ctrl *c = a.ctrl;
@@ -234,9 +247,162 @@ __global__ void __launch_bounds__(256) k_filter(IterArgs a) {
     // pad to a multiple of 4 with sentinels that can never win (d = inf, strict '<') so k_gn scans in chunks of 4
     const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);  // k_gn scans 2, then chunks of 4
     if (lane < padded - base) out[base + lane] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-    if (lane == 0) { a.ccount[b] = padded; kept += (unsigned long long)base; }
+    if (lane == 0) {
+      a.ccount[b] = padded;
+      kept += (unsigned long long)base;
+      if (a.ball) { a.cbase[b] = base; a.ball[b] = make_float4(qx, qy, qz, rho); }  // what this list is exact for (k_filter_reuse)
+    }
   }
   if (lane == 0 && kept) atomicAdd(&a.ctrl->kept_total, kept);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_filter_reuse: the same exact pruning, fed from the PREVIOUS iteration's pruned list where that is provably enough.
+// The list of iteration e-1 is exact for every query inside the ball (centre query, rho) it was built for.  If the ball of
+// iteration e lies inside it, the nearest candidate of every query of iteration e -- and of the new centre query -- is in
+// that list, so pruning it instead of the K-slot row yields the same exact superset (a subsequence, so slot order and the
+// ascending-norm property are kept) for a fraction of the HBM traffic.  Measured at configs[1]: the particle cloud contracts
+// monotonically and every row takes this path from iteration 2 on.  Rows that fail the containment test (NaN included)
+// are pruned from the full row.
+// Mapping: a warp takes 32 consecutive rows.  Rows whose previous list is short (<= FR_FAST entries: almost all of them
+// once the cloud has contracted) are pruned by ONE THREAD each -- a warp per row would spend ~250 issue slots on three
+// candidates, which made the kernel issue bound at ~60 us.  The remaining rows (long lists, failed containment) are then
+// pruned one after the other by the whole warp, exactly like k_filter.
+// ---------------------------------------------------------------------------------------------
+#ifndef SVN_FR_FAST
+#define SVN_FR_FAST 256  // measured at configs[1] (late iterations, ncu): 16 -> 30 us (the few long rows serialise whole warps), 128+ -> 19 us
+#endif
+constexpr int FR_FAST = SVN_FR_FAST;
+
+struct FrRow {
+  float qx, qy, qz, rho;
+  bool from_prev;
+  int n_prev;
+};
+
+__device__ __forceinline__ FrRow fr_row_setup(const IterArgs &a, const float *A, const float *tb, float alpha, float beta, int b) {
+  const Ctrl *c = a.ctrl;
+  const float4 s = a.sp[b];
+  const float4 pb = a.ball_prev[b];
+  FrRow r;
+  r.n_prev = a.cbase_prev[b];
+  r.qx = fmaf(A[0], s.x, fmaf(A[1], s.y, fmaf(A[2], s.z, tb[0])));
+  r.qy = fmaf(A[3], s.x, fmaf(A[4], s.y, fmaf(A[5], s.z, tb[1])));
+  r.qz = fmaf(A[6], s.x, fmaf(A[7], s.y, fmaf(A[8], s.z, tb[2])));
+  float rho = fmaf(alpha, s.w, beta);
+  const int rbin = (int)(s.w * (float)(1.0 / PRUNE_BIN_W));
+  if (rbin < PRUNE_BINS) rho = fminf(rho, c->env[rbin]);
+  r.rho = rho;
+  const float cx = r.qx - pb.x, cy = r.qy - pb.y, cz = r.qz - pb.z;
+  const float move = sqrtf(fmaf(cz, cz, fmaf(cy, cy, cx * cx)));
+  r.from_prev = fmaf(move, 1.00001f, rho) + 1e-6f <= pb.w;  // ball(q', rho) inside ball(q_prev, rho_prev); NaN -> false
+  return r;
+}
+
+__global__ void __launch_bounds__(256, 4) k_filter_reuse(IterArgs a) {
+  if (a.ctrl->stop) return;
+  if (!filter_use_reuse(a)) return;  // k_filter (streaming, warp per row) takes this iteration
+  __shared__ unsigned long long s_kept;
+  if (threadIdx.x == 0) s_kept = 0ull;
+  __syncthreads();
+  const int lane = lane_id();
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const Ctrl *c = a.ctrl;
+  float A[9], tb[3];
+#pragma unroll
+  for (int i = 0; i < 9; i++) A[i] = c->Abar[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) tb[i] = c->taubar[i];
+  const float alpha = c->alpha, beta = c->beta;
+  const int K = a.K, Kp = a.Kp;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned long long kept = 0;
+  for (int b0 = gw * 32; b0 < a.n_s; b0 += nw * 32) {
+    const int b = b0 + lane;
+    const bool valid = b < a.n_s;
+    FrRow r;
+    r.from_prev = false;
+    r.n_prev = 0;
+    if (valid) r = fr_row_setup(a, A, tb, alpha, beta, b);
+    const bool fast = valid && r.from_prev && r.n_prev <= FR_FAST;
+    if (fast) {
+      // ---- one thread, one row: two passes over <= FR_FAST entries (the second one hits L1)
+      const float4 *prow = a.clist_prev + (size_t)b * Kp;
+      float dmin = INFINITY;
+      for (int k = 0; k < r.n_prev; k++) {
+        const float4 e = prow[k];
+        const float dx = r.qx - e.x, dy = r.qy - e.y, dz = r.qz - e.z;
+        dmin = fminf(dmin, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+      }
+      const float lim = sqrtf(dmin) + 2.0f * r.rho + PRUNE_MARGIN;
+      const float thr = lim * lim * (1.0f + 1e-5f);
+      float4 *out = a.clist + (size_t)b * Kp;
+      int base = 0;
+      for (int k = 0; k < r.n_prev; k++) {
+        const float4 e = prow[k];
+        const float dx = r.qx - e.x, dy = r.qy - e.y, dz = r.qz - e.z;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (!(d2 > thr)) out[base++] = e;
+      }
+      const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);
+      for (int k = base; k < padded; k++) out[k] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+      a.ccount[b] = padded;
+      a.cbase[b] = base;
+      a.ball[b] = make_float4(r.qx, r.qy, r.qz, r.rho);
+      kept += (unsigned long long)base + (1ull << 40);  // high bits: rows served by the previous list
+    }
+    // ---- the other rows, one after the other, by the whole warp (as k_filter)
+    unsigned slow = __ballot_sync(0xffffffffu, valid && !fast);
+    while (slow) {
+      const int src_lane = __ffs(slow) - 1;
+      slow &= slow - 1;
+      const int bb = b0 + src_lane;
+      const float qx = __shfl_sync(0xffffffffu, r.qx, src_lane), qy = __shfl_sync(0xffffffffu, r.qy, src_lane);
+      const float qz = __shfl_sync(0xffffffffu, r.qz, src_lane), rho = __shfl_sync(0xffffffffu, r.rho, src_lane);
+      const bool from_prev = __shfl_sync(0xffffffffu, (int)r.from_prev, src_lane) != 0;
+      const int n_src = from_prev ? __shfl_sync(0xffffffffu, r.n_prev, src_lane) : K;
+      const float4 *row = from_prev ? a.clist_prev + (size_t)bb * Kp : a.cand + (size_t)bb * K;
+      float dmin = INFINITY;
+      for (int k = lane; k < n_src; k += 32) {
+        const float4 e = row[k];
+        const float dx = qx - e.x, dy = qy - e.y, dz = qz - e.z;
+        dmin = fminf(dmin, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+      }
+      dmin = warp_min(dmin);
+      const float lim = sqrtf(dmin) + 2.0f * rho + PRUNE_MARGIN;
+      const float thr = lim * lim * (1.0f + 1e-5f);
+      float4 *out = a.clist + (size_t)bb * Kp;
+      int base = 0;
+      for (int k0 = 0; k0 < n_src; k0 += 32) {
+        const int k = k0 + lane;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool keep = false;
+        if (k < n_src) {
+          e = row[k];
+          const float dx = qx - e.x, dy = qy - e.y, dz = qz - e.z;
+          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          keep = !(d2 > thr);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[base + __popc(m & lt)] = e;
+        base += __popc(m);
+      }
+      const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);
+      if (lane < padded - base) out[base + lane] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+      if (lane == 0) {
+        a.ccount[bb] = padded;
+        a.cbase[bb] = base;
+        a.ball[bb] = make_float4(qx, qy, qz, rho);
+        kept += (unsigned long long)base + (from_prev ? (1ull << 40) : 0ull);
+      }
+    }
+  }
+  // one global atomic per CTA (the statistic is not worth thousands of same-address atomics per launch)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+  if (lane == 0 && kept) atomicAdd(&s_kept, kept);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_kept) atomicAdd(&a.ctrl->kept_total, s_kept);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -545,6 +711,14 @@ int launch_filter(const IterArgs &a, cudaStream_t st) {
   const int max_grid = a.sm_count * 8;
   if (grid > max_grid) grid = max_grid;
   if (grid < 1) grid = 1;
+  int launches = 1;
+  if (a.clist_prev) {  // iterations >= 1: both pruning kernels are enqueued, filter_use_reuse() lets exactly one of them work
+    int g = cdiv(a.n_s, 32 * 8);  // a warp takes 32 consecutive rows per trip
+    const int resident = a.sm_count * 4;  // __launch_bounds__(256, 4): one wave, grid-stride over the rows
+    if (g > resident) g = resident;
+    k_filter_reuse<<<g < 1 ? 1 : g, 256, 0, st>>>(a);
+    launches = 2;
+  }
   switch (nch) {
     case 1: k_filter<1><<<grid, 256, 0, st>>>(a); break;
     case 2: k_filter<2><<<grid, 256, 0, st>>>(a); break;
@@ -555,7 +729,7 @@ int launch_filter(const IterArgs &a, cudaStream_t st) {
     case 7: k_filter<7><<<grid, 256, 0, st>>>(a); break;
     default: k_filter<8><<<grid, 256, 0, st>>>(a); break;
   }
-  return 1;
+  return launches;
 }
 
 int launch_gn(const IterArgs &a, cudaStream_t st) {

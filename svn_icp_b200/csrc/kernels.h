@@ -44,6 +44,14 @@ struct IterArgs {
   int pair_mode;        // 1: clist/ccount hold the interleaved pair lists of gn_pair.cu
   float4 *clist;
   int *ccount;
+  // list reuse (k_filter): the previous iteration's pruned lists, their true lengths and the ball (centre query, radius)
+  // they are exact for; null = always prune from the full table.  cbase / ball: the same for THIS iteration's output.
+  const float4 *clist_prev;
+  const int *cbase_prev;
+  const float4 *ball_prev;
+  int *cbase;
+  float4 *ball;
+  const unsigned long long *kept_hist;  // [I] kept candidates per iteration (low 40 bits): picks the pruning kernel, see filter_use_reuse
   double *R, *t;       // [P][9], [P][3]
   float *xf;           // [P_l][12]
   double *dnorm;       // [P_l]

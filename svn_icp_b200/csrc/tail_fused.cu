@@ -582,8 +582,7 @@ int launch_tail_fused(const SteinArgs &a, const IterArgs &ia, cudaStream_t st) {
   if (max_blocks_per_sm < 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, k_tail_fused, TF_THREADS, 0);
   if (max_blocks_per_sm < 1) return -1;
   int grid = a.sm_count;  // one CTA per SM: all co-resident, as the grid barriers require
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_tail_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024); attr = true; }
+  cudaFuncSetAttribute(k_tail_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024);  // per device; cheap, so every launch
   int xs_bytes = 6 * a.P * (int)sizeof(double);
   if (xs_bytes > 160 * 1024 || a.P < 2) xs_bytes = 0;  // large P: read x through L2 instead
   void *args[] = {(void *)&a, (void *)&ia, (void *)&xs_bytes};
