@@ -188,7 +188,7 @@ __device__ __forceinline__ bool filter_use_reuse(const IterArgs &a) {
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(256) k_filter(IterArgs a) {
+__global__ void __launch_bounds__(256, 4) k_filter(IterArgs a) {  // 64 registers: four CTAs per SM keep the HBM pipe full
   if (a.ctrl->stop) return;
   if (filter_use_reuse(a)) return;  // k_filter_reuse takes this iteration
   const int lane = lane_id();
