@@ -381,6 +381,37 @@ def main():
                                                phases_ms_per_scan=ph_gd, mean=[float(v) for v in mean_gd])
         icp_gd.close()
 
+    # The reference ITSELF on this GPU: its unmodified SVNICP sources + its vendored knn.cu against
+    # libtorch CUDA (oracle/_ref/libsvnicp_ref_cuda.so, built by oracle/build_ref_cuda.sh), same scan, same particles, in a
+    # subprocess (its O(P*N_s) fp64 temporaries peak at ~83 GB; a failure there must not take this bench down).  Also the
+    # full-size parity figure: our particles against the reference's on the BASELINE-size problem.
+    reference_on_gpu = None
+    if world == 1 and not args.no_variants:
+        ref_so = os.path.join(ROOT, "oracle", "_ref", "libsvnicp_ref_cuda.so")
+        if os.path.exists(ref_so):
+            out_npy = os.path.join(ROOT, "gpurun_out", "ref_gpu_particles.npy")
+            os.makedirs(os.path.dirname(out_npy), exist_ok=True)
+            try:
+                r = subprocess.run([sys.executable, "-m", "oracle.ref_gpu_run", str(P), str(I), "0", out_npy], cwd=ROOT, capture_output=True,
+                                   text=True, timeout=420)
+                reference_on_gpu = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as exc:  # noqa: BLE001
+                reference_on_gpu = dict(ok=False, error=f"{type(exc).__name__}: {str(exc)[:200]}")
+            if reference_on_gpu.get("ok"):
+                icp.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, pb.init_pose)
+                icp.set_initial_mean(pb.R0, pb.t0)
+                icp.stein_align()
+                ours = icp.get_particles().reshape(6, P)
+                theirs = np.load(out_npy)
+                reference_on_gpu.update(
+                    scans_per_sec=1.0 / reference_on_gpu["seconds_scan"],
+                    speedup_device=(args.steps / (ms_dev * 1e-3)) * reference_on_gpu["seconds_scan"],
+                    parity_full_size=dict(max_abs_particle_diff=float(np.nanmax(np.abs(ours - theirs))),
+                                          max_abs_mean_diff=float(np.max(np.abs(icp.get_transformation() - np.array(reference_on_gpu["mean"])))),
+                                          note="our scan vs the reference's own GPU run, same inputs, 30 iterations, all particles"))
+        else:
+            reference_on_gpu = dict(ok=False, error="oracle/_ref/libsvnicp_ref_cuda.so not built (oracle/build_ref_cuda.sh needs /root/reference)")
+
     if rank == 0:
         h2d = (n_s + n_t) * 24 + 6 * P * 8
         d2h = (48 + 6 * P) * 8
@@ -394,6 +425,8 @@ def main():
                     gpu_launches=int(launches), roofline=roofline, clocks=clocks,
                     phases_ms_per_scan=ph, scan_info=info, prune_mean_kept=[round(float(x), 2) for x in prune], variants=variants,
                     check=dict(mean=[float(v) for v in out[0]], gt=[float(v) for v in pb.gt_rel]), datagen_s=gen_s)
+        if reference_on_gpu is not None:
+            line["reference_on_gpu"] = reference_on_gpu
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(pb)
         print(json.dumps(line))

@@ -343,13 +343,21 @@ def ref_available() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libsvnicp_ref.so"))
 
 
+def ref_cuda_available() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libsvnicp_ref_cuda.so"))
+
+
 class Reference:
     """The reference's own registration classes (CPU device swap).  One (P, threshold) per PROCESS
-    (function-static tensors, SVNICP.cpp:42,167) -- run each configuration in a fresh subprocess."""
+    (function-static tensors, SVNICP.cpp:42,167) -- run each configuration in a fresh subprocess.
+    cuda=True loads oracle/_ref/libsvnicp_ref_cuda.so instead (oracle/build_ref_cuda.sh): the same sources WITHOUT the
+    device swap plus the reference's vendored knn.cu, i.e. the reference as it runs on a GPU (bench comparator only)."""
 
-    def __init__(self):
+    def __init__(self, cuda: bool = False):
         import torch  # noqa: F401  (libtorch must be loaded first)
-        self.lib = C.CDLL(os.path.join(HERE, "_ref", "libsvnicp_ref.so"))
+        if cuda:
+            torch.zeros(1).cuda()  # CUDA context + libtorch_cuda loaded before the reference library
+        self.lib = C.CDLL(os.path.join(HERE, "_ref", "libsvnicp_ref_cuda.so" if cuda else "libsvnicp_ref.so"))
         self.lib.ref_num_threads.restype = C.c_int
 
     def num_threads(self):

@@ -29,6 +29,21 @@
 #undef private
 #undef protected
 
+// -DREF_CUDA (oracle/build_ref_cuda.sh): no device swap and the reference's OWN vendored CUDA K-NN (knn.cu) -- the
+// reference as it runs on a GPU, for bench.py's `reference_on_gpu` comparator.  Inputs are moved to the device, results
+// are read back through host(), and the timers synchronise the device.
+#ifdef REF_CUDA
+#include <torch/cuda.h>
+static inline at::Tensor host(const at::Tensor &t) { return t.to(torch::kCPU).contiguous(); }
+static inline at::Tensor dev(const at::Tensor &t) { return t.to(torch::kCUDA); }
+static inline void dsync() { torch::cuda::synchronize(); }
+#else
+static inline at::Tensor host(const at::Tensor &t) { return t.contiguous(); }
+static inline at::Tensor dev(const at::Tensor &t) { return t; }
+static inline void dsync() {}
+#endif
+
+#ifndef REF_CUDA
 // ------------------------------------------------------------------------------------------
 std::tuple<at::Tensor, at::Tensor> KNearestNeighborIdx(const at::Tensor &p1_, const at::Tensor &p2_,
                                                        const at::Tensor &lengths1, const at::Tensor &lengths2,
@@ -71,6 +86,7 @@ std::tuple<at::Tensor, at::Tensor> KNearestNeighborIdx(const at::Tensor &p1_, co
   });
   return std::make_tuple(idxs, dists);
 }
+#endif  // !REF_CUDA
 
 // ------------------------------------------------------------------------------------------
 extern "C" {
@@ -110,13 +126,13 @@ static gtsam::Pose3 *make_pose(const double *R0_rowmajor, const double *t0) {
 }
 
 static at::Tensor blob(const double *p, std::vector<int64_t> shape) {
-  return torch::from_blob(const_cast<double *>(p), shape, torch::TensorOptions().dtype(torch::kFloat64)).clone();
+  return dev(torch::from_blob(const_cast<double *>(p), shape, torch::TensorOptions().dtype(torch::kFloat64)).clone());
 }
 
 static void getters(svnicp::SVNICP &icp, int P, int I, double *particles, double *mean, double *var,
                     double *cov, double *weights, float *history) {
-  const auto m = icp.get_transformation().contiguous();
-  const auto v = icp.get_distribution().contiguous();
+  const auto m = host(icp.get_transformation());
+  const auto v = host(icp.get_distribution());
   const auto c = icp.get_cov_matrix();
   const auto pp = icp.get_particles();
   const auto w = icp.get_particle_weight();
@@ -143,11 +159,14 @@ int ref_scan(const ref_params *prm, const double *src, int64_t n_s, const double
   svnicp::ParticleWeightOpt opt;
   svnicp::SVNICP icp(cfg, init, opt);
   const auto s = blob(src, {n_s, 3}), t = blob(tgt, {n_t, 3});
+  dsync();
   const auto T0 = std::chrono::steady_clock::now();
   icp.add_cloud(s, t, init.clone());
   icp.set_initial_mean(*make_pose(R0, t0));
+  dsync();
   const auto T1 = std::chrono::steady_clock::now();
   const int state = icp.stein_align();
+  dsync();
   const auto T2 = std::chrono::steady_clock::now();
   getters(icp, P, prm->iterations, particles, mean, var, cov, weights, history);
   const auto T3 = std::chrono::steady_clock::now();
@@ -184,7 +203,7 @@ int ref_scan_steps(const ref_params *prm, const double *src, int64_t n_s, const 
       // replay the head of the iteration with the object's own methods (SVNICP.cpp:50-71)
       const auto [mb, tb] = icp.mini_batch_pair_generator();
       if (cand_idx && it == 0)
-        std::memcpy(cand_idx, icp.sourceKNN_idx_.contiguous().data_ptr<int64_t>(), sizeof(int64_t) * n_s * cfg.KNN_count);
+        std::memcpy(cand_idx, host(icp.sourceKNN_idx_).data_ptr<int64_t>(), sizeof(int64_t) * n_s * cfg.KNN_count);
       const auto mbe = mb[0].expand({P, (int64_t)n_s, 3});
       const auto Rtot = icp.R0_.matmul(icp.R_);
       const auto ttot = icp.t0_ + icp.R0_.matmul(icp.t_);
@@ -193,10 +212,10 @@ int ref_scan_steps(const ref_params *prm, const double *src, int64_t n_s, const 
       const auto tr = mbe.matmul(Rtot.transpose(1, 2)) + ttot.view({P, 1, 3});
       const auto [sp, trp, tp] = icp.get_correspondence_fast(mbe, tr, tb[0]);
       const auto [ng_, H, b] = icp.Newton_grad_right(sp, trp, tp);
-      if (Hd) std::memcpy(Hd + (size_t)it * P * 36, H.contiguous().data_ptr<double>(), sizeof(double) * P * 36);
-      if (bd) std::memcpy(bd + (size_t)it * P * 6, b.contiguous().data_ptr<double>(), sizeof(double) * P * 6);
-      if (tgt_paired) std::memcpy(tgt_paired + (size_t)it * P * n_s * 3, tp.contiguous().data_ptr<double>(), sizeof(double) * P * n_s * 3);
-      if (src_tr) std::memcpy(src_tr + (size_t)it * P * n_s * 3, trp.contiguous().data_ptr<double>(), sizeof(double) * P * n_s * 3);
+      if (Hd) std::memcpy(Hd + (size_t)it * P * 36, host(H).data_ptr<double>(), sizeof(double) * P * 36);
+      if (bd) std::memcpy(bd + (size_t)it * P * 6, host(b).data_ptr<double>(), sizeof(double) * P * 6);
+      if (tgt_paired) std::memcpy(tgt_paired + (size_t)it * P * n_s * 3, host(tp).data_ptr<double>(), sizeof(double) * P * n_s * 3);
+      if (src_tr) std::memcpy(src_tr + (size_t)it * P * n_s * 3, host(trp).data_ptr<double>(), sizeof(double) * P * n_s * 3);
     }
     state = icp.stein_align();
     if (x_after) {
@@ -228,8 +247,8 @@ int ref_svgd_scan(const ref_params *prm, const char *optimizer, const double *sr
     icp.set_initial_mean(*make_pose(R0, t0));
     state = icp.stein_align();
   }
-  const auto m = icp.get_transformation().contiguous();
-  const auto v = icp.get_distribution().contiguous();
+  const auto m = host(icp.get_transformation());
+  const auto v = host(icp.get_distribution());
   const auto c = icp.get_cov_matrix();
   const auto pp = icp.get_particles();
   const auto w = icp.get_particle_weight();
