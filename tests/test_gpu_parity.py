@@ -306,3 +306,55 @@ def test_pair_mode_same_bits(oracle, lidar, monkeypatch, odd):
     cidx, rel = icp.get_candidates(want_rel=True)
     oidx, omask = oracle.corr_f32(res["pair"][0], icp.get_source_f32(), rel, cidx, 3.0)
     np.testing.assert_array_equal(res["pair"][1], oidx)
+
+
+def test_list_reuse_same_bits(lidar, monkeypatch):
+    """k_filter_reuse (pruning the previous iteration's lists once they are short) must choose exactly the same
+    correspondences as pruning the full K-slot table every iteration (SVNICP_FILTER_FULL=1): bit-identical poses."""
+    res = {}
+    for mode in ("reuse", "full"):
+        if mode == "full":
+            monkeypatch.setenv("SVNICP_FILTER_FULL", "1")
+        else:
+            monkeypatch.delenv("SVNICP_FILTER_FULL", raising=False)
+        icp = sv.SVNICP(sv.SteinICPParam(iterations=25, KNN_count=100, max_dist=3.0, lr=1.0), lidar.init_pose)
+        icp.add_cloud(lidar.source, lidar.target, lidar.init_pose)
+        icp.set_initial_mean(lidar.R0, lidar.t0)
+        icp.stein_align()
+        monkeypatch.setenv("SVNICP_DEBUG_REUSE", "1")
+        hits = icp.get_prune_stats()
+        monkeypatch.delenv("SVNICP_DEBUG_REUSE")
+        res[mode] = (icp.get_particles(), icp.get_particle_history(), hits)
+    np.testing.assert_array_equal(res["reuse"][0], res["full"][0])
+    np.testing.assert_array_equal(res["reuse"][1], res["full"][1])
+    assert res["reuse"][2][-1] > 0.99 and res["full"][2].max() == 0.0  # the reuse path really ran in the late iterations
+
+
+def test_against_the_reference_running_on_this_gpu(tmp_path):
+    """The reference's OWN sources + its vendored knn.cu built against libtorch CUDA (oracle/_ref/libsvnicp_ref_cuda.so, built
+    where /root/reference exists) run the same scan on this GPU in a subprocess; our particles must agree within the scan
+    tolerance and the mean within POSE_TOL.  (bench.py reports the same figure at the full BASELINE size.)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    import bench
+    if not orc.ref_cuda_available():
+        pytest.skip("oracle/_ref/libsvnicp_ref_cuda.so not built")
+    P, I, cap = 64, 12, 6000
+    out_npy = os.path.join(tmp_path, "ref_particles.npy")
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_gpu_run", str(P), str(I), str(cap), out_npy], cwd=bench.ROOT, capture_output=True,
+                       text=True, timeout=600)
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info.get("ok"), info
+    pb, _ = bench.make_problem(P)
+    src = bench._subsample(pb, cap)
+    W = bench.WORKLOAD
+    icp = sv.SVNICP(sv.SteinICPParam(iterations=I, KNN_count=W["K"], max_dist=W["max_dist"], lr=W["lr"], SVN_full_grad=W["svn_full_grad"]),
+                    pb.init_pose)
+    icp.add_cloud(src, pb.target, pb.init_pose)
+    icp.set_initial_mean(pb.R0, pb.t0)
+    assert icp.stein_align() == sv.ALIGN_SUCCESS
+    theirs = np.load(out_npy)
+    np.testing.assert_allclose(icp.get_particles().reshape(6, P), theirs, atol=5 * POSE_TOL, rtol=0)
+    np.testing.assert_allclose(icp.get_transformation(), np.array(info["mean"]), atol=POSE_TOL, rtol=0)
