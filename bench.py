@@ -191,11 +191,22 @@ def main():
     ap.add_argument("--particles", type=int, default=WORKLOAD["particles"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--config", type=int, default=1, choices=(1, 2),
+                    help="BASELINE.json configs index: 1 = the contract workload (default); 2 = 128-beam ~260k-point scan, 4096 particles "
+                         "(the sharded parity/scaling case; not the driver's bench line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     WORKLOAD["particles"] = args.particles
+    global METRIC
+    workload_name = "configs[1]: 64-beam synthetic scan, 1000 particles, particle-sharded when N>1"
+    if args.config == 2:
+        WORKLOAD.update(sensor="128", particles=4096 if args.particles == 1000 else args.particles)
+        METRIC = "scans/sec at 4096 particles (128-beam ~260k-pt synthetic scan, K=100, 30 SVN iterations)"
+        workload_name = "configs[2]: 128-beam synthetic scan, 4096 particles, particle-sharded when N>1"
+        args.no_variants = True
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -418,7 +429,7 @@ def main():
         line = dict(metric=METRIC, value=args.steps / (ms_dev * 1e-3), unit="scans/sec", n_gpus=world, steps=args.steps, warmup=W,
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32 geometry / f64 reduction+Stein",
                     data="synthetic",
-                    config=dict(workload="configs[1]: 64-beam synthetic scan, 1000 particles, particle-sharded when N>1", n_s=n_s, n_t=n_t,
+                    config=dict(workload=workload_name, n_s=n_s, n_t=n_t,
                                 l2="candidate table 16*N_s*K bytes > 126 MB L2 is re-streamed every iteration; inputs are not L2 resident",
                                 particles_per_gpu=P_g, **WORKLOAD),
                     e2e=dict(value=args.steps / (ms_e2e * 1e-3), unit="scans/sec", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
