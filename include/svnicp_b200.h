@@ -189,6 +189,30 @@ int svnicp_map_download(svnicp_map m, double *out_xyz, int64_t n);
 /* Size() / Empty() (VoxelHashMap.h:55-56): live voxels and stored points */
 int svnicp_map_size(svnicp_map m, int64_t *voxels, int64_t *points);
 
+/* ---------------------------------------------------------------------------------------------
+ * Scan pre-processing on the device, the step right before add_cloud in the reference's node
+ * (OdometryPipeline.cpp:555-560): crop_pointcloud (:692-704) and downsample_uniform (:684-690 =
+ * pcl::UniformSampling, leaf = the radius argument).  Clouds are float xyz triples (pcl::PointXYZI without the
+ * intensity).  Outputs live in buffers owned by the handle and stay valid until the next-but-one call on it, so
+ * crop -> downsample -> downsample chains without copies; an output may be fed to svnicp_map_add_cloud (float, device)
+ * or, through svnicp_pre_to_f64, to svnicp_add_cloud (double, device).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct svnicp_pre_t *svnicp_pre;
+int svnicp_pre_create(svnicp_pre *out, int64_t max_points, int device);
+void svnicp_pre_destroy(svnicp_pre p);
+const char *svnicp_pre_last_error(svnicp_pre p);
+/* crop_pointcloud: keeps min_range^2 < |p|^2 < max_range^2 in input order.  *max_sq_norm = max |p|^2 over ALL input
+ * points: the reference keeps the running maximum of this SQUARED norm in scan_max_range_ (:699). */
+int svnicp_pre_crop(svnicp_pre p, const float *xyz, int64_t n, int on_device, double min_range, double max_range,
+                    const float **dev_out, int64_t *n_out, double *max_sq_norm);
+/* downsample_uniform(cloud, voxel_size): one point per leaf of size `leaf`; PCL's rule (distance to the leaf's integer
+ * index, first point on ties).  Output order is arbitrary (PCL iterates an unordered_map). */
+int svnicp_pre_downsample_uniform(svnicp_pre p, const float *xyz, int64_t n, int on_device, double leaf, const float **dev_out,
+                                  int64_t *n_out);
+/* float device cloud -> double device cloud (owned by the handle) for svnicp_add_cloud(source_on_device = 1) */
+int svnicp_pre_to_f64(svnicp_pre p, const float *dev_xyz, int64_t n, const double **dev_out);
+int svnicp_pre_download(svnicp_pre p, const float *dev_xyz, int64_t n, float *out);
+
 #ifdef __cplusplus
 }
 #endif

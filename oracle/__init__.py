@@ -44,7 +44,7 @@ def _ptr(a):
 
 def build(force: bool = False) -> str:
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("svn_oracle.c", "svgd_oracle.c", "voxelmap_oracle.c")]
+    srcs = [os.path.join(HERE, f) for f in ("svn_oracle.c", "svgd_oracle.c", "voxelmap_oracle.c", "preprocess_oracle.c")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -305,6 +305,28 @@ class VoxelMapOracle:
 
     def Clear(self):
         self.lib.oracle_vmap_clear(self.m)
+
+
+class PreprocessOracle:
+    """Sequential restatement of the node's crop + pcl::UniformSampling (preprocess_oracle.c; down-sampling parity unpinned)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(build())
+        self.lib.oracle_crop.restype = C.c_int64
+        self.lib.oracle_downsample_uniform.restype = C.c_int64
+
+    def crop(self, cloud, min_range, max_range):
+        a = np.ascontiguousarray(cloud, dtype=np.float32)
+        out = np.zeros_like(a)
+        mx = C.c_double(0)
+        n = self.lib.oracle_crop(_ptr(a), C.c_int64(len(a)), C.c_double(min_range), C.c_double(max_range), _ptr(out), C.byref(mx))
+        return out[:n].copy(), mx.value
+
+    def downsample_uniform(self, cloud, radius):
+        a = np.ascontiguousarray(cloud, dtype=np.float32)
+        out = np.zeros_like(a)
+        n = self.lib.oracle_downsample_uniform(_ptr(a), C.c_int64(len(a)), C.c_double(radius), _ptr(out))
+        return out[:n].copy()
 
 
 class ReferenceMap:

@@ -76,6 +76,8 @@ EXPORTS = [
     "svnicp_get_scan_info", "svnicp_get_tail_stamps",
     "svnicp_map_create", "svnicp_map_destroy", "svnicp_map_last_error", "svnicp_map_clear", "svnicp_map_add_cloud", "svnicp_map_get",
     "svnicp_map_download", "svnicp_map_size",
+    "svnicp_pre_create", "svnicp_pre_destroy", "svnicp_pre_last_error", "svnicp_pre_crop", "svnicp_pre_downsample_uniform",
+    "svnicp_pre_to_f64", "svnicp_pre_download",
 ]
 
 
@@ -91,8 +93,13 @@ def load_library() -> C.CDLL:
         lib.svnicp_last_error.argtypes = [C.c_void_p]
         for name in EXPORTS:
             fn = getattr(lib, name)
-            if name not in ("svnicp_last_error", "svnicp_destroy", "svnicp_default_params", "svnicp_map_last_error", "svnicp_map_destroy"):
+            if name not in ("svnicp_last_error", "svnicp_destroy", "svnicp_default_params", "svnicp_map_last_error", "svnicp_map_destroy",
+                            "svnicp_pre_last_error", "svnicp_pre_destroy"):
                 fn.restype = C.c_int
+        lib.svnicp_pre_destroy.restype = None
+        lib.svnicp_pre_destroy.argtypes = [C.c_void_p]
+        lib.svnicp_pre_last_error.restype = C.c_char_p
+        lib.svnicp_pre_last_error.argtypes = [C.c_void_p]
         lib.svnicp_destroy.restype = None
         lib.svnicp_destroy.argtypes = [C.c_void_p]
         lib.svnicp_map_destroy.restype = None
@@ -440,4 +447,68 @@ class VoxelHashMap:
         _, n = self.GetMapDevice(position, max_range)
         out = np.zeros((n, 3))
         self._check(self._lib.svnicp_map_download(self._m, _p(out), C.c_int64(n)), "GetMap")
+        return out
+
+
+class ScanPreprocessor:
+    """The node's scan pre-processing on the device (OdometryPipeline.cpp:555-560): `crop_pointcloud` (:692-704) and
+    `downsample_uniform` (:684-690, pcl::UniformSampling).  Methods return (device pointer to [n,3] float32, n); feed one to the
+    next method with on_device=True, to VoxelHashMap.AddPointCloudDevice, or through `to_f64` to SVNICP.add_cloud_device."""
+
+    def __init__(self, max_points: int, device: int = -1):
+        self._lib = load_library()
+        self._p = C.c_void_p()
+        self.scan_max_range_ = 0.0  # the reference's running maximum of the SQUARED norm (OdometryPipeline.cpp:699)
+        rc = self._lib.svnicp_pre_create(C.byref(self._p), C.c_int64(max_points), C.c_int(device))
+        if rc != 0:
+            self._p = C.c_void_p()
+            raise SvnIcpError(f"svnicp_pre_create failed ({rc}): " + (self._lib.svnicp_pre_last_error(None) or b"").decode())
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise SvnIcpError(f"{what} failed ({rc}): " + (self._lib.svnicp_pre_last_error(self._p) or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_p", None) and self._p.value:
+            self._lib.svnicp_pre_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _src(cloud, n, on_device):
+        if on_device:
+            return C.c_void_p(cloud), int(n), None
+        a = np.ascontiguousarray(cloud, dtype=np.float32)
+        return _p(a), len(a), a
+
+    def crop_pointcloud(self, cloud, min_range: float, max_range: float, n: int = 0, on_device: bool = False):
+        src, n, keep = self._src(cloud, n, on_device)
+        ptr, n_out, mx = C.c_void_p(), C.c_int64(0), C.c_double(0)
+        self._check(self._lib.svnicp_pre_crop(self._p, src, C.c_int64(n), C.c_int(int(on_device)), C.c_double(min_range), C.c_double(max_range),
+                                              C.byref(ptr), C.byref(n_out), C.byref(mx)), "crop_pointcloud")
+        if mx.value > self.scan_max_range_:
+            self.scan_max_range_ = mx.value
+        return ptr.value, n_out.value
+
+    def downsample_uniform(self, cloud, voxel_size: float, n: int = 0, on_device: bool = False):
+        src, n, keep = self._src(cloud, n, on_device)
+        ptr, n_out = C.c_void_p(), C.c_int64(0)
+        self._check(self._lib.svnicp_pre_downsample_uniform(self._p, src, C.c_int64(n), C.c_int(int(on_device)), C.c_double(voxel_size),
+                                                            C.byref(ptr), C.byref(n_out)), "downsample_uniform")
+        return ptr.value, n_out.value
+
+    def to_f64(self, ptr: int, n: int) -> int:
+        out = C.c_void_p()
+        self._check(self._lib.svnicp_pre_to_f64(self._p, C.c_void_p(ptr), C.c_int64(n), C.byref(out)), "to_f64")
+        return out.value
+
+    def download(self, ptr: int, n: int) -> np.ndarray:
+        out = np.zeros((n, 3), dtype=np.float32)
+        self._check(self._lib.svnicp_pre_download(self._p, C.c_void_p(ptr), C.c_int64(n), _p(out)), "download")
         return out

@@ -1,3 +1,7 @@
+// host-only check of the header-only mirrors: the stein_msgs producer mapping runs here; the other two headers only have
+// to compile and link against the C ABI (they need a GPU to run: tests/test_cpp_mirror.py, tests/test_preprocess.py)
+#include "svnicp/ScanPreprocessor.hpp"
+#include "svnicp/VoxelHashMap.hpp"
 #include "svnicp/stein_msgs_compat.hpp"
 int main() {
   using namespace svnicp;
