@@ -43,7 +43,7 @@ def lidar():
     return synth.make_problem(64, sensor="32", scan_index=6, n_map_scans=6, seed=0xC0FFEE)
 
 
-@pytest.mark.parametrize("which,K", [("small", 20), ("small", 100), ("lidar", 100), ("lidar", 33)])
+@pytest.mark.parametrize("which,K", [("small", 20), ("small", 100), ("lidar", 100), ("lidar", 33), ("lidar", 256), ("small", 1)])
 def test_candidate_table_exact(oracle, request, which, K):
     """Per-scan K-NN: same K-nearest SET as the reference's brute force (MinK), emitted ascending (d0^2, index)."""
     pb = request.getfixturevalue(which)
@@ -187,6 +187,23 @@ def test_full_scan_vs_oracle(oracle, lidar, full):
     # and the scan actually registers: mean close to the planted relative motion
     assert np.abs(icp.get_transformation() - lidar.gt_rel)[:3].max() < 0.05
     assert np.abs(icp.get_transformation() - lidar.gt_rel)[3:].max() < 0.005
+
+
+@pytest.mark.parametrize("K", [1, 7, 256])
+def test_scan_extreme_candidate_counts(oracle, small, K):
+    """KNN_count at the edges of the supported range (1 = plain nearest point of the initial guess, 256 = the ABI maximum,
+    7 = not a multiple of 4: padded list rows)."""
+    rng = np.random.default_rng(K)
+    P = 16
+    init = synth.init_particles(P, rng)
+    icp = sv.SVNICP(sv.SteinICPParam(iterations=4, KNN_count=K, max_dist=3.0, lr=1.0), init)
+    icp.add_cloud(small.source, small.target, init)
+    icp.set_initial_mean(small.R0, small.t0)
+    assert icp.stein_align() == sv.ALIGN_SUCCESS
+    prm = orc.make_params(iterations=4, knn_count=K, max_dist=3.0, lr=1.0)
+    o = oracle.align(prm, small.source, small.target, init, small.R0, small.t0)
+    np.testing.assert_allclose(icp.get_particles().reshape(6, P), o["particles"], rtol=0, atol=5 * POSE_TOL)
+    np.testing.assert_allclose(icp.get_transformation(), o["mean"], rtol=0, atol=POSE_TOL)
 
 
 @pytest.mark.parametrize("name", golden_names())
