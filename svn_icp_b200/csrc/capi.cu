@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -98,6 +100,10 @@ struct svnicp_handle_t {
   DevBuf<float4> clist2, ball[2];
   DevBuf<int> ccount2, cbase[2];
   int filter_reuse = 1;
+  // internal particle order (compute_particle_order): internal index i holds the caller's particle perm[i]
+  std::vector<int> perm;
+  std::vector<double> perm_stage;
+  bool permuted = false;
   int pair_mode = 0;
   int rows_per_rank = 0;
   DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc, cand_idx;
@@ -200,10 +206,46 @@ static SvgdArgs svgd_args(svnicp_handle h) {
   return s;
 }
 
+// Internal particle order.  The particle -> thread (and, sharded, particle -> GPU) assignment is free, and k_gn's exact early
+// exit is a WARP vote: 32 particles that sit close together in pose space agree earlier, and a rank whose slice is a compact
+// cluster gets a smaller pruning ball.  So the particles are laid out in Morton order of (x, y, yaw) quantised to 3 bits
+// each (measured at configs[1]: k_gn 30.7 -> 28.4 ms per scan); every getter maps back to the caller's order.  The Stein step
+// sums over all particles either way; only the order of its fp64 sums changes.  SVNICP_NO_PARTICLE_SORT=1 keeps the
+// caller's order (A/B measurements).  Not applied to the SVGD-ICP class (its pose_particles_ state spans scans).
+static void compute_particle_order(svnicp_handle h, const double *init_pose) {
+  const int P = h->P;
+  h->perm.resize(P);
+  for (int p = 0; p < P; p++) h->perm[p] = p;
+  h->permuted = false;
+  if (!init_pose || P < 64 || h->class_type != SVNICP_CLASS_SVNICP || getenv("SVNICP_NO_PARTICLE_SORT")) return;
+  const int comps[3] = {0, 1, 5};
+  std::vector<int> code(P, 0);
+  for (int j = 0; j < 3; j++) {
+    const double *v = init_pose + (size_t)comps[j] * P;
+    double lo = v[0], hi = v[0];
+    for (int p = 1; p < P; p++) { lo = v[p] < lo ? v[p] : lo; hi = v[p] > hi ? v[p] : hi; }
+    if (!(hi > lo) || !std::isfinite(hi - lo)) continue;
+    for (int p = 0; p < P; p++) {
+      int q = (int)((v[p] - lo) / (hi - lo) * 8.0);
+      q = q < 0 ? 0 : (q > 7 ? 7 : q);
+      for (int b = 0; b < 3; b++) code[p] |= ((q >> b) & 1) << (3 * b + j);
+    }
+  }
+  std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) { return code[a] < code[b]; });
+  for (int p = 0; p < P; p++)
+    if (h->perm[p] != p) { h->permuted = true; break; }
+}
+
 static int upload_particles(svnicp_handle h, const double *init_pose) {
   const size_t n = (size_t)6 * h->P;
   CU(h->init_pose.ensure(n));
-  if (init_pose) CU(cudaMemcpyAsync(h->init_pose.p, init_pose, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  compute_particle_order(h, init_pose);
+  if (init_pose && h->permuted) {
+    h->perm_stage.resize(n);
+    for (int c = 0; c < 6; c++)
+      for (int i = 0; i < h->P; i++) h->perm_stage[(size_t)c * h->P + i] = init_pose[(size_t)c * h->P + h->perm[i]];
+    CU(cudaMemcpyAsync(h->init_pose.p, h->perm_stage.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  } else if (init_pose) CU(cudaMemcpyAsync(h->init_pose.p, init_pose, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   else CU(cudaMemsetAsync(h->init_pose.p, 0, n * sizeof(double), h->stream));
   if (h->class_type == SVNICP_CLASS_SVGDICP) {
     SvgdArgs s = svgd_args(h);
@@ -753,7 +795,12 @@ int svnicp_get_cov_matrix(svnicp_handle h, double out36[36]) {
 }
 int svnicp_get_particles(svnicp_handle h, double *out) {
   NEED_ALIGNED();
-  memcpy(out, h->h_particles, (size_t)6 * h->P * sizeof(double));
+  if (!h->permuted) {
+    memcpy(out, h->h_particles, (size_t)6 * h->P * sizeof(double));
+  } else {  // back to the caller's particle order
+    for (int c = 0; c < 6; c++)
+      for (int i = 0; i < h->P; i++) out[(size_t)c * h->P + h->perm[i]] = h->h_particles[(size_t)c * h->P + i];
+  }
   return SVNICP_OK;
 }
 int svnicp_get_particle_weight(svnicp_handle h, double *out) {
@@ -771,6 +818,14 @@ int svnicp_get_particle_history(svnicp_handle h, float *out, int32_t *rows) {
   if (out && I > 0) {
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpy(out, h->history.p, (size_t)I * 6 * h->P * sizeof(float), cudaMemcpyDeviceToHost));
+    if (h->permuted) {  // rows are [6][P] in internal order: back to the caller's particle order
+      std::vector<float> row((size_t)h->P);
+      for (size_t r = 0; r < (size_t)I * 6; r++) {
+        float *p = out + r * h->P;
+        memcpy(row.data(), p, (size_t)h->P * sizeof(float));
+        for (int i = 0; i < h->P; i++) p[h->perm[i]] = row[i];
+      }
+    }
   }
   return SVNICP_OK;
 }
@@ -850,9 +905,19 @@ int svnicp_get_correspondences(svnicp_handle h, float *out_xf, int32_t *out_idx,
   if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
   if (!h->prm.debug_corr) return fail(h, SVNICP_ERR_INVALID, "created without debug_corr");
   CU(cudaSetDevice(h->device));
-  if (out_xf) CU(cudaMemcpy(out_xf, h->dbg_xf.p, (size_t)h->P_l * 12 * sizeof(float), cudaMemcpyDeviceToHost));
-  if (out_idx) CU(cudaMemcpy(out_idx, h->dbg_idx.p, (size_t)h->P_l * h->n_s * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (out_mask) CU(cudaMemcpy(out_mask, h->dbg_mask.p, (size_t)h->P_l * h->n_s, cudaMemcpyDeviceToHost));
+  // rows are local particles in INTERNAL order; on an unsharded handle they are handed out in the caller's order
+  const bool unperm = h->permuted && h->n_ranks == 1;
+  auto fetch_rows = [&](void *out, const void *dev, size_t row_bytes) -> cudaError_t {
+    if (!unperm) return cudaMemcpy(out, dev, (size_t)h->P_l * row_bytes, cudaMemcpyDeviceToHost);
+    std::vector<unsigned char> tmp((size_t)h->P_l * row_bytes);
+    const cudaError_t e = cudaMemcpy(tmp.data(), dev, tmp.size(), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < h->P_l; i++) memcpy((unsigned char *)out + (size_t)h->perm[i] * row_bytes, tmp.data() + (size_t)i * row_bytes, row_bytes);
+    return cudaSuccess;
+  };
+  if (out_xf) CU(fetch_rows(out_xf, h->dbg_xf.p, 12 * sizeof(float)));
+  if (out_idx) CU(fetch_rows(out_idx, h->dbg_idx.p, (size_t)h->n_s * sizeof(int32_t)));
+  if (out_mask) CU(fetch_rows(out_mask, h->dbg_mask.p, (size_t)h->n_s));
   return SVNICP_OK;
 }
 
@@ -864,14 +929,15 @@ int svnicp_get_gn_system(svnicp_handle h, double *out_H, double *out_b, double *
   // x at the head of the last executed iteration lives in xs [6][P] (the epilogue rewrites rec's x with the final poses)
   std::vector<double> xs((size_t)6 * h->P);
   CU(cudaMemcpy(xs.data(), h->xs.p, xs.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  for (int p = 0; p < h->P; p++) {
-    const double *r = rec.data() + (size_t)p * REC;
+  for (int i = 0; i < h->P; i++) {  // i: internal order, p: the caller's particle index
+    const double *r = rec.data() + (size_t)i * REC;
+    const size_t p = h->permuted ? (size_t)h->perm[i] : (size_t)i;
     if (out_x)
-      for (int c = 0; c < 6; c++) out_x[6 * (size_t)p + c] = xs[(size_t)c * h->P + p];
-    if (out_b) memcpy(out_b + 6 * (size_t)p, r + REC_B, 6 * sizeof(double));
+      for (int c = 0; c < 6; c++) out_x[6 * p + c] = xs[(size_t)c * h->P + i];
+    if (out_b) memcpy(out_b + 6 * p, r + REC_B, 6 * sizeof(double));
     if (out_H)
       for (int a = 0; a < 6; a++)
-        for (int c = 0; c < 6; c++) out_H[36 * (size_t)p + 6 * a + c] = r[REC_H + (a <= c ? tri(a, c) : tri(c, a))];
+        for (int c = 0; c < 6; c++) out_H[36 * p + 6 * a + c] = r[REC_H + (a <= c ? tri(a, c) : tri(c, a))];
   }
   return SVNICP_OK;
 }
@@ -879,7 +945,15 @@ int svnicp_get_gn_system(svnicp_handle h, double *out_H, double *out_b, double *
 int svnicp_get_stein(svnicp_handle h, double *out_delta, double *out_bandwidth) {
   if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
   CU(cudaSetDevice(h->device));
-  if (out_delta) CU(cudaMemcpy(out_delta, h->delta.p, (size_t)h->P_l * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_delta) {
+    if (h->permuted && h->n_ranks == 1) {  // unsharded: the caller's particle order (sharded: the local slice in internal order)
+      std::vector<double> tmp((size_t)h->P_l * 6);
+      CU(cudaMemcpy(tmp.data(), h->delta.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < h->P_l; i++) memcpy(out_delta + 6 * (size_t)h->perm[i], tmp.data() + 6 * (size_t)i, 6 * sizeof(double));
+    } else {
+      CU(cudaMemcpy(out_delta, h->delta.p, (size_t)h->P_l * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+  }
   if (out_bandwidth) *out_bandwidth = h->h_ctrl->bandwidth;
   return SVNICP_OK;
 }
