@@ -164,7 +164,7 @@ def run_reference(args, rank, world):
         call(prm, src)
         return time.time() - t0
 
-    ns1, ns2 = 128, 256
+    ns1, ns2 = 256, 512  # measured on the 16-core GPU box: 10 steps + 3 warm-ups of this sample take about 40 s
     for _ in range(max(args.warmup, 1)):
         run(ns1, 1)
     vals, desc = [], ""
