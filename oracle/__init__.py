@@ -245,6 +245,13 @@ class Oracle:
         self.lib.oracle_svgd_step(_ptr(x), _ptr(g), C.c_int(len(x)), _ptr(out), C.byref(h))
         return out, h.value
 
+    def opt_step(self, optimizer: str, lr, step, x, grad, state):
+        """torch::optim step (SVGDICP.cpp:142-170 options) on flat arrays, in place: x [n], grad [n], state [n][2]."""
+        assert x.dtype == np.float64 and state.dtype == np.float64 and x.flags.c_contiguous and state.flags.c_contiguous
+        g = _f64(grad).reshape(-1)
+        self.lib.oracle_opt_step_array(C.c_int(OPTIMIZERS[optimizer]), C.c_double(lr), C.c_int(step), _ptr(x), _ptr(g), _ptr(state),
+                                       C.c_int64(x.size))
+
     def euler_R(self, r, p, y):
         R = np.zeros(9)
         self.lib.oracle_euler_R(C.c_double(r), C.c_double(p), C.c_double(y), _ptr(R))

@@ -190,6 +190,11 @@ void oracle_opt_step(int opt, double lr, int step, double *p, double grad, doubl
   }
 }
 
+/* n scalars at once (tests of the sharded host logic): x [n], grad [n], st [n][2] updated in place */
+void oracle_opt_step_array(int opt, double lr, int step, double *x, const double *grad, double *st, int64_t n) {
+  for (int64_t i = 0; i < n; i++) oracle_opt_step(opt, lr, step, x + i, grad[i], st + 2 * i);
+}
+
 static void svgd_getters(const double *x /*[P][6]*/, int P, double *particles, double *mean, double *var,
                          double *cov, double *weights) {
   for (int p = 0; p < P; p++)
