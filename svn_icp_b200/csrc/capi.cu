@@ -217,25 +217,29 @@ static void compute_particle_order(svnicp_handle h, const double *init_pose) {
   h->perm.resize(P);
   for (int p = 0; p < P; p++) h->perm[p] = p;
   h->permuted = false;
-  // Unsharded handles only.  Measured on 8 GPUs at configs[1]: with the order applied across ranks each rank's slice is a
-  // compact cluster (kept candidates 72 -> 47, k_gn 4.34 -> 3.94 ms per scan) but the clusters differ in cost, and the wait at
-  // the per-iteration all-gather grows from 0.9 to 2.2 ms: 95.6 -> 90.5 scans/s.  (Ordering inside each rank's slice is the
-  // variant to try next.)
-  if (!init_pose || P < 64 || h->n_ranks > 1 || h->class_type != SVNICP_CLASS_SVNICP || getenv("SVNICP_NO_PARTICLE_SORT")) return;
+  // Sharded handles: the order is applied INSIDE each rank's slice, so every rank keeps the same (representative) particles
+  // it had before.  Measured on 8 GPUs at configs[1] with the order applied ACROSS ranks instead: each slice becomes a compact
+  // cluster (kept candidates 72 -> 47, k_gn 4.34 -> 3.94 ms per scan) but the clusters differ in cost and the wait at the
+  // per-iteration all-gather grows from 0.9 to 2.2 ms: 95.6 -> 90.5 scans/s.
+  if (!init_pose || P < 64 || h->class_type != SVNICP_CLASS_SVNICP || getenv("SVNICP_NO_PARTICLE_SORT")) return;
   const int comps[3] = {0, 1, 5};
   std::vector<int> code(P, 0);
-  for (int j = 0; j < 3; j++) {
-    const double *v = init_pose + (size_t)comps[j] * P;
-    double lo = v[0], hi = v[0];
-    for (int p = 1; p < P; p++) { lo = v[p] < lo ? v[p] : lo; hi = v[p] > hi ? v[p] : hi; }
-    if (!(hi > lo) || !std::isfinite(hi - lo)) continue;
-    for (int p = 0; p < P; p++) {
-      int q = (int)((v[p] - lo) / (hi - lo) * 8.0);
-      q = q < 0 ? 0 : (q > 7 ? 7 : q);
-      for (int b = 0; b < 3; b++) code[p] |= ((q >> b) & 1) << (3 * b + j);
+  for (int blk = 0; blk < h->n_ranks; blk++) {  // identical on every rank: depends on init_pose and the slice bounds only
+    const int b_lo = blk * h->P_l_max, b_hi = std::min(P, b_lo + h->P_l_max);
+    if (b_hi - b_lo < 64) continue;
+    for (int j = 0; j < 3; j++) {
+      const double *v = init_pose + (size_t)comps[j] * P;
+      double lo = v[b_lo], hi = v[b_lo];
+      for (int p = b_lo + 1; p < b_hi; p++) { lo = v[p] < lo ? v[p] : lo; hi = v[p] > hi ? v[p] : hi; }
+      if (!(hi > lo) || !std::isfinite(hi - lo)) continue;
+      for (int p = b_lo; p < b_hi; p++) {
+        int q = (int)((v[p] - lo) / (hi - lo) * 8.0);
+        q = q < 0 ? 0 : (q > 7 ? 7 : q);
+        for (int b = 0; b < 3; b++) code[p] |= ((q >> b) & 1) << (3 * b + j);
+      }
     }
+    std::stable_sort(h->perm.begin() + b_lo, h->perm.begin() + b_hi, [&](int a, int b) { return code[a] < code[b]; });
   }
-  std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) { return code[a] < code[b]; });
   for (int p = 0; p < P; p++)
     if (h->perm[p] != p) { h->permuted = true; break; }
 }
