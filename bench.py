@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- scans/sec of the SVN-ICP registration inner loop on N B200s (one process per GPU).
 
-  python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--config 1|2|3|4]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one scan: add_cloud -> set_initial_mean -> stein_align -> getters (the call sequence of the
@@ -11,9 +11,11 @@ reference's caller, OdometryPipeline.cpp:582-607) on BASELINE.json configs[1]: s
   e2e         the same scan through the public API with HOST (pinned) clouds: H2D copies and result D2H inside the timing
   roofline    correspondence+reduction pass (k_filter + k_gn): algorithmic bytes / measured device time vs measured HBM peak
   cpu_baseline  the CPU checker timed on this box's host cores on a bounded sample (reported baseline, not the target)
-With N > 1 the particles are sharded across the ranks (strong scaling of the same scan; one ncclAllGather per iteration).
+  check       N > 1: rank 0 repeats the last scan on an unsharded handle and reports |sharded - single| (asserted <= 1e-7)
+With N > 1 the particles are sharded across the ranks (strong scaling of the same scan; one record exchange per iteration).
 --impl reference times the reference's own CPU implementation (oracle/_ref, libtorch on all host cores; the C port if
-_ref is absent) on a bounded sample of the same workload and prints the same JSON line.
+_ref is absent) on a bounded sample of the same workload and prints the same JSON line (same `config`).
+--config 2/3/4: the other BASELINE.json configurations (parity / scaling / stress cases; not the driver's bench line).
 """
 from __future__ import annotations
 
@@ -33,6 +35,23 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(sensor="64", particles=1000, iterations=30, K=100, max_dist=3.0, lr=1.0, svn_full_grad=True,
                 scan_index=8, n_map_scans=8)
 METRIC = "scans/sec at 1000 particles (64-beam ~120k-pt synthetic scan, K=100, 30 SVN iterations)"
+WORKLOAD_NAME = "configs[1]: 64-beam synthetic scan, 1000 particles, particle-sharded when N>1"
+SHARD_TOL = 1e-7  # N-GPU vs 1-GPU particles (identical algorithm; only the grouping of fp32 partial sums depends on the slice)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def bench_config(n_s: int, n_t: int, world: int) -> dict:
+    """The `config` object of the JSON line: built by this one function for BOTH arms, so they are identical."""
+    P = WORKLOAD["particles"]
+    return dict(workload=WORKLOAD_NAME, n_s=int(n_s), n_t=int(n_t),
+                l2="candidate table 16*N_s*K bytes > 126 MB L2 is re-streamed every iteration; inputs are not L2 resident",
+                particles_per_gpu=-(-P // max(world, 1)), **WORKLOAD)
 
 
 def peaks():
@@ -59,7 +78,7 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
-        except Exception:
+        except Exception:  # noqa: BLE001
             self.proc = None
 
     def _read(self):
@@ -72,7 +91,7 @@ class ClockSampler:
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
-        except Exception:
+        except Exception:  # noqa: BLE001
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -83,32 +102,18 @@ class ClockSampler:
                 for n, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
-            except Exception:
+            except Exception:  # noqa: BLE001
                 pass
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
                     samples=len(sm))
 
 
-def make_problem(P, seed=0xC0FFEE):
+def make_problem(P, seed=0xC0FFEE, scan_index=None):
     from svn_icp_b200 import synth
     t = time.time()
-    pb = synth.make_problem_saturated(P, sensor=WORKLOAD["sensor"], scan_index=WORKLOAD["scan_index"], seed=seed)
+    pb = synth.make_problem_saturated(P, sensor=WORKLOAD["sensor"], scan_index=WORKLOAD["scan_index"] if scan_index is None else scan_index,
+                                      seed=seed)
     return pb, time.time() - t
-
-
-def _sampled_scan_time(run, ns_full, I, ns1, ns2):
-    """Affine model of the CPU scan time from four bounded runs: T(n_s, iters) = setup(n_s) + iters * (a + b n_s).
-    setup (the brute-force K-NN) and b (correspondence + Gauss-Newton) scale with N_s, a (the P x P Stein step) does not.
-    run(ns, iters) -> seconds.  Returns (t_scan_full, description)."""
-    T22, T21, T12, T11 = run(ns2, 2), run(ns2, 1), run(ns1, 2), run(ns1, 1)
-    it2, it1 = max(T22 - T21, 1e-9), max(T12 - T11, 1e-9)
-    b = max((it2 - it1) / (ns2 - ns1), 0.0)
-    a = max(it2 - b * ns2, 0.0)
-    setup2 = max(T21 - it2, 0.0)
-    t_scan = setup2 * ns_full / ns2 + I * (a + b * ns_full)
-    desc = (f"runs at N_s={ns1},{ns2} x iterations=1,2: setup {setup2:.2f}s@{ns2} pts, per iteration {a:.3f}s (Stein, N_s-independent) + "
-            f"{b * 1e3:.3f} ms/point; extrapolated to N_s={ns_full}, {I} iterations")
-    return t_scan, desc
 
 
 def _subsample(pb, ns, seed=1):
@@ -116,72 +121,151 @@ def _subsample(pb, ns, seed=1):
     return pb.source[sel]
 
 
-def cpu_baseline_port(pb):
-    """The C restatement (OpenMP, all host cores) on a bounded sample of the same workload (all particles, the full map,
-    subsets of the source points, 1-2 iterations), extrapolated with the affine model above."""
+def _oracle_params(iters):
+    import oracle as orc
+    return orc.make_params(iterations=iters, knn_count=WORKLOAD["K"], max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"],
+                           svn_full_grad=WORKLOAD["svn_full_grad"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU legs (test infrastructure: the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_baseline_port(pb, cand_idx):
+    """The C restatement (OpenMP, all host cores).  MEASURED: one full-size Gauss-Newton iteration (all particles x all
+    source points, the reference's 1-NN among K candidates + robust H, b) and one full-size Stein step.  The per-scan
+    brute-force K-NN is timed on a row subset and scaled by the row count (every query row is an independent identical
+    sweep over the whole map, so this leg is exactly linear).  scan = knn + iterations * (gn + stein)."""
     import oracle as orc
     O = orc.Oracle()
-    K, I = WORKLOAD["K"], WORKLOAD["iterations"]
+    cores = host_cores()
+    O.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: set the thread count explicitly
+    P, I, K = pb.init_pose.shape[1], WORKLOAD["iterations"], WORKLOAD["K"]
+    n_s = len(pb.source)
+    R = np.stack([O.so3_exp(pb.init_pose[3:, p])[0] for p in range(P)])
+    t = np.ascontiguousarray(pb.init_pose[:3].T)
+    sub = 4096
+    q0 = O.transform_q0(pb.source[:sub], pb.R0, pb.t0)
+    O.knn_mink(q0[:256], pb.target, K)  # warm-up: thread pool, page-in of the map
+    t0 = time.time()
+    O.knn_mink(q0, pb.target, K)
+    t_knn_sub = time.time() - t0
+    t0 = time.time()
+    H, b = O.gn(R, t, pb.R0, pb.t0, pb.source, pb.target, cand_idx, WORKLOAD["max_dist"])[:2]
+    t_gn = time.time() - t0
+    x = np.concatenate([t, np.zeros((P, 3))], axis=1)
+    t0 = time.time()
+    O.stein_step(x, H, b, full=WORKLOAD["svn_full_grad"], lr=WORKLOAD["lr"])
+    t_stein = time.time() - t0
+    t_knn = t_knn_sub * n_s / sub
+    t_scan = t_knn + I * (t_gn + t_stein)
+    return dict(value=1.0 / t_scan, unit="scans/sec", cores=O.num_threads(), kind="port", sampled=True,
+                measured_s=dict(gn_one_full_iteration=t_gn, stein_one_step=t_stein, knn_rows=sub, knn_subset=t_knn_sub),
+                extrapolated=dict(knn_full_s=t_knn, scan_s=t_scan, rule="knn * N_s/rows + iterations * (gn + stein)"),
+                sample=f"C port (OpenMP, {O.num_threads()} threads): ONE full-size iteration measured (all {P} particles x all {n_s} "
+                       f"points x K={K}: {t_gn:.1f}s) + one Stein step ({t_stein:.2f}s); brute-force K-NN timed on {sub} of {n_s} rows "
+                       f"against the full {len(pb.target)}-point map ({t_knn_sub:.1f}s) and scaled by rows; scan = knn + {I} x (gn + stein)")
 
-    def run_once(ns, iters):
-        prm = orc.make_params(iterations=iters, knn_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], svn_full_grad=WORKLOAD["svn_full_grad"])
-        src = _subsample(pb, ns)
-        t0 = time.time()
-        O.align(prm, src, pb.target, pb.init_pose, pb.R0, pb.t0)
-        return time.time() - t0
 
-    def run(ns, iters):  # best of two: the four timings are differenced, so one-off stalls (thread-pool start, page faults) matter
-        return min(run_once(ns, iters), run_once(ns, iters))
-
-    run_once(256, 1)  # warm-up: OpenMP thread pool, page-in of the map
-    t_scan, desc = _sampled_scan_time(run, len(pb.source), I, 1024, 2048)
-    return dict(value=1.0 / t_scan, unit="scans/sec", cores=O.num_threads(), kind="port",
-                sample=f"C port (OpenMP): all {pb.init_pose.shape[1]} particles, full {len(pb.target)}-point map; " + desc)
+def cpu_config0(kind="port"):
+    """BASELINE.json configs[0] in FULL on the host cores (no sampling): 100 particles, the voxel-down-sampled scan
+    (uniform 0.5 m then 1.5 m, OdometryPipeline.cpp:559-560), full local map, 30 iterations."""
+    import oracle as orc
+    from svn_icp_b200 import synth
+    pb, _ = make_problem(100)
+    ds = np.ascontiguousarray(synth.uniform_downsample(synth.uniform_downsample(pb.source, 0.5), 1.5))
+    prm = _oracle_params(WORKLOAD["iterations"])
+    cores = host_cores()
+    if kind == "reference":
+        eng = orc.Reference()
+        eng.set_num_threads(cores)
+        call = lambda: eng.scan(prm, ds, pb.target, pb.init_pose, pb.R0, pb.t0)
+    else:
+        eng = orc.Oracle()
+        eng.set_num_threads(cores)
+        call = lambda: eng.align(prm, ds, pb.target, pb.init_pose, pb.R0, pb.t0)
+    call()
+    t0 = time.time()
+    out = call()
+    dt = time.time() - t0
+    mean = out["mean"] if isinstance(out, dict) and "mean" in out else None
+    return dict(workload="configs[0]: 100 particles, voxel-down-sampled 64-beam scan", n_s=int(len(ds)), n_t=int(len(pb.target)),
+                particles=100, iterations=WORKLOAD["iterations"], seconds_per_scan=dt, scans_per_sec=1.0 / dt, cores=eng.num_threads(),
+                kind=kind, sampled=False, mean=[float(v) for v in mean] if mean is not None else None)
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own sources on the host cores (oracle/_ref; the C port if absent), bounded sample per step."""
+    """--impl reference: the reference's own sources on the host cores (oracle/_ref; the C port if absent).  A step is a
+    bounded sample of the bench workload (all particles, the full map, two source subsets x 1 and 2 iterations); the
+    per-scan time follows from T(n_s, iters) = setup(n_s) + iters * (a + b n_s), fitted on the MEDIANS over the steps."""
     if rank != 0:
         return
     import oracle as orc
     P = WORKLOAD["particles"]
     pb, _ = make_problem(P)
-    K, I = WORKLOAD["K"], WORKLOAD["iterations"]
+    I = WORKLOAD["iterations"]
     ns_full = len(pb.source)
+    cores = host_cores()
     if orc.ref_available():
         eng = orc.Reference()
-        kind, cores = "reference", eng.num_threads()
+        kind = "reference"
         call = lambda prm, src: eng.scan(prm, src, pb.target, pb.init_pose, pb.R0, pb.t0)
     else:
         eng = orc.Oracle()
-        kind, cores = "port", eng.num_threads()
+        kind = "port"
         call = lambda prm, src: eng.align(prm, src, pb.target, pb.init_pose, pb.R0, pb.t0)
+    eng.set_num_threads(cores)  # explicit: torchrun exports OMP_NUM_THREADS=1
 
     def run(ns, iters):
-        prm = orc.make_params(iterations=iters, knn_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], svn_full_grad=WORKLOAD["svn_full_grad"])
         src = _subsample(pb, ns)
         t0 = time.time()
-        call(prm, src)
+        call(_oracle_params(iters), src)
         return time.time() - t0
 
-    ns1, ns2 = 256, 512  # measured on the 16-core GPU box: 10 steps + 3 warm-ups of this sample take about 40 s
+    ns1, ns2 = 256, 1024  # ~5 s per step on a 16-core host
     for _ in range(max(args.warmup, 1)):
         run(ns1, 1)
-    vals, desc = [], ""
-    for _ in range(args.steps):  # a step = one bounded sample (4 short runs) -> one extrapolated scan time
-        t_scan, desc = _sampled_scan_time(run, ns_full, I, ns1, ns2)
-        vals.append(t_scan)
-    t_scan = float(np.mean(vals))
+    T = dict(a22=[], a21=[], a12=[], a11=[])
+    t_begin = time.time()
+    steps_done = 0
+    for _ in range(args.steps):  # a step = one bounded sample (4 short runs)
+        T["a22"].append(run(ns2, 2)); T["a21"].append(run(ns2, 1)); T["a12"].append(run(ns1, 2)); T["a11"].append(run(ns1, 1))
+        steps_done += 1
+        if time.time() - t_begin > 240.0:  # time box: the whole arm must end within a few minutes on any host
+            break
+    wall = time.time() - t_begin
+    T22, T21, T12, T11 = (float(np.median(T[k])) for k in ("a22", "a21", "a12", "a11"))
+    it2, it1 = max(T22 - T21, 1e-9), max(T12 - T11, 1e-9)
+    b = max((it2 - it1) / (ns2 - ns1), 0.0)
+    a = max(it2 - b * ns2, 0.0)
+    setup2 = max(T21 - it2, 0.0)
+    t_scan = setup2 * ns_full / ns2 + I * (a + b * ns_full)
+    spread = float(np.std([x - y for x, y in zip(T["a22"], T["a21"])]) / it2) if steps_done > 1 else 0.0
     val = 1.0 / t_scan
-    sample = f"{kind} (libtorch CPU, device-swapped reference sources): all {P} particles, full {len(pb.target)}-point map; " + desc
-    line = dict(metric=METRIC, value=val, unit="scans/sec", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=t_scan * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                impl="reference", config=dict(workload="configs[1]: 64-beam synthetic scan, 1000 particles", n_s=ns_full, n_t=len(pb.target), **WORKLOAD),
-                cpu_baseline=dict(value=val, unit="scans/sec", cores=cores, kind=kind, sample=sample),
+    sample = (f"{kind} ({'libtorch CPU, device-swapped reference sources' if kind == 'reference' else 'C port'}, {eng.num_threads()} threads): "
+              f"all {P} particles, full {len(pb.target)}-point map; per step 4 runs at N_s={ns1},{ns2} x iterations=1,2 (medians over "
+              f"{steps_done} steps): setup {setup2:.2f}s@{ns2} pts, per iteration {a:.3f}s (Stein, N_s-independent) + {b * 1e3:.3f} ms/point; "
+              f"extrapolated to N_s={ns_full}, {I} iterations")
+    line = dict(metric=METRIC, value=val, unit="scans/sec", n_gpus=args.gpus, steps=steps_done, warmup=args.warmup,
+                ms_per_step=wall / max(steps_done, 1) * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                impl="reference", sampled=True, config=bench_config(ns_full, len(pb.target), args.gpus),
+                extrapolated=dict(scan_s=t_scan, ms_per_scan=t_scan * 1e3, rel_spread_of_iteration_time=spread,
+                                  note="ms_per_step is the wall time of one bounded sample (what was timed); value = 1 / extrapolated full-scan time"),
+                cpu_baseline=dict(value=val, unit="scans/sec", cores=eng.num_threads(), kind=kind, sample=sample, sampled=True),
                 e2e=dict(value=val, unit="scans/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    # configs[0] is small enough to be MEASURED in full on the host (separate process: the reference freezes the particle
+    # count in function-static tensors, SVNICP.cpp:42,167)
+    if not args.no_variants:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-config0", kind], cwd=ROOT, capture_output=True, text=True, timeout=600)
+            line["config0_full_measurement"] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as exc:  # noqa: BLE001
+            line["config0_full_measurement"] = dict(error=f"{type(exc).__name__}: {str(exc)[:200]}")
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,22 +275,28 @@ def main():
     ap.add_argument("--particles", type=int, default=WORKLOAD["particles"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
-    ap.add_argument("--config", type=int, default=1, choices=(1, 2),
-                    help="BASELINE.json configs index: 1 = the contract workload (default); 2 = 128-beam ~260k-point scan, 4096 particles "
-                         "(the sharded parity/scaling case; not the driver's bench line)")
+    ap.add_argument("--cpu-config0", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--config", type=int, default=1, choices=(1, 2, 3, 4),
+                    help="BASELINE.json configs index: 1 = the contract workload (default); 2 = 128-beam ~260k-point scan, 4096 particles; "
+                         "3 = throughput mode, 8 independent streams x 256 particles per GPU; 4 = 10M-point map, 16384 particles")
     args = ap.parse_args()
+    if args.cpu_config0:
+        print(json.dumps(cpu_config0(args.cpu_config0)))
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     WORKLOAD["particles"] = args.particles
-    global METRIC
-    workload_name = "configs[1]: 64-beam synthetic scan, 1000 particles, particle-sharded when N>1"
+    global METRIC, WORKLOAD_NAME
     if args.config == 2:
         WORKLOAD.update(sensor="128", particles=4096 if args.particles == 1000 else args.particles)
         METRIC = "scans/sec at 4096 particles (128-beam ~260k-pt synthetic scan, K=100, 30 SVN iterations)"
-        workload_name = "configs[2]: 128-beam synthetic scan, 4096 particles, particle-sharded when N>1"
+        WORKLOAD_NAME = "configs[2]: 128-beam synthetic scan, 4096 particles, particle-sharded when N>1"
         args.no_variants = True
         args.no_cpu_baseline = True
+    if args.config in (3, 4):
+        import bench_extra
+        return bench_extra.run(args, rank, world, local_rank)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -229,26 +319,31 @@ def main():
     from svn_icp_b200 import synth
     particles = [synth.init_particles(P, rng) for _ in range(W + args.steps + 2)]
 
-    prm = sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], SVN_full_grad=WORKLOAD["svn_full_grad"],
-                           check_early_stop=False)
-    icp = sv.SVNICP(prm, particles[0], device=local_rank)
-    if world > 1:
-        uid = [sv.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        icp.init_sharding(uid[0], rank, world)
+    def new_handle(flags=0, sharded=True, **kw):
+        prm = sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"], SVN_full_grad=WORKLOAD["svn_full_grad"],
+                               check_early_stop=False, flags=flags, **kw)
+        h = sv.SVNICP(prm, particles[0], device=local_rank)
+        if world > 1 and sharded:
+            uid = [sv.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            h.init_sharding(uid[0], rank, world)
+        h.set_stream(stream.cuda_stream)
+        return h
+
     stream = torch.cuda.current_stream()
-    icp.set_stream(stream.cuda_stream)
+    icp = new_handle()
 
     src_dev = torch.from_numpy(pb.source).to(dev)
     tgt_dev = torch.from_numpy(pb.target).to(dev)
     src_pin = torch.from_numpy(pb.source).pin_memory()
     tgt_pin = torch.from_numpy(pb.target).pin_memory()
 
-    def scan_device(i):
-        icp.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, particles[i])
-        icp.set_initial_mean(pb.R0, pb.t0)
-        assert icp.stein_align() == sv.ALIGN_SUCCESS
-        return icp.get_transformation(), icp.get_distribution(), icp.get_cov_matrix(), icp.get_particles()
+    def scan_device(i, h=None):
+        h = h or icp
+        h.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, particles[i])
+        h.set_initial_mean(pb.R0, pb.t0)
+        assert h.stein_align() == sv.ALIGN_SUCCESS
+        return h.get_transformation(), h.get_distribution(), h.get_cov_matrix(), h.get_particles()
 
     def scan_host(i):
         icp.add_cloud_pinned(src_pin.data_ptr(), n_s, tgt_pin.data_ptr(), n_t, particles[i])
@@ -284,8 +379,23 @@ def main():
     ms_dev, out = timed(scan_device, W, args.steps)
     launches = icp.launch_count() * args.steps
     clocks = sampler.stop() if rank == 0 else None
+    last_hist, last_iters = icp.get_particle_history(), icp.iterations_done()
     scan_host(0)
     ms_e2e, out_h = timed(scan_host, W, args.steps)
+
+    # N > 1: the same scan (the last timed one) on an UNSHARDED handle on rank 0 -- the driver-visible multi-GPU parity figure
+    check = dict(mean=[float(v) for v in out[0]], gt=[float(v) for v in pb.gt_rel])
+    if world > 1:
+        if rank == 0:
+            single = new_handle(sharded=False)
+            o1 = scan_device(W + args.steps - 1, single)
+            d_part = float(np.nanmax(np.abs(o1[3] - out[3])))
+            d_hist = float(np.nanmax(np.abs(single.get_particle_history() - last_hist)))
+            check["sharded_vs_single_max_abs"] = dict(particles=d_part, history_f32=d_hist, mean=float(np.max(np.abs(o1[0] - out[0]))),
+                                                      cov=float(np.max(np.abs(o1[2] - out[2]))), iterations=[int(last_iters), int(single.iterations_done())],
+                                                      tolerance=SHARD_TOL, ok=bool(d_part <= SHARD_TOL and last_iters == single.iterations_done()))
+            single.close()
+        barrier()
 
     # per-phase device times of one profiled scan (events around each launch group): the roofline numerators
     icp.set_profiling(True)
@@ -298,45 +408,41 @@ def main():
     P_g = hi - lo
     hbm_peak, peak_src, sm_max = peaks()
     iters = max(ph["iterations"], 1)
-    # algorithmic bytes / flops per iteration per GPU (restated in DESIGN.md)
+    # algorithmic bytes per iteration per GPU (restated in DESIGN.md)
     b_alg = 16.0 * n_s * (1 + K) + 156.0 * P_g
-    f_alg = float(P_g) * n_s * (130.0 + 8.0 * K)
     t_pass = (ph["filter_ms"] + ph["gn_ms"]) / iters * 1e-3
-    # the HBM-streaming kernel alone: from iteration ~11 on the default path prunes the previous iteration's short lists
+    # the HBM-streaming kernel alone: once the lists are short the default path prunes the previous iteration's lists
     # instead of streaming the K-slot table (k_filter_reuse), so its bytes/time is measured on a scan that streams the
-    # table every iteration (SVNICP_FILTER_FULL=1, read at add_cloud)
-    os.environ["SVNICP_FILTER_FULL"] = "1"
-    icp_ff = sv.SVNICP(prm, particles[0], device=local_rank)
-    if world > 1:
-        uid = [sv.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        icp_ff.init_sharding(uid[0], rank, world)
-    icp_ff.set_stream(stream.cuda_stream)
+    # table every iteration (SVNICP_FLAG_FILTER_FULL)
+    icp_ff = new_handle(flags=sv.FLAG_FILTER_FULL)
     icp_ff.set_profiling(True)
     for _ in range(2):
-        icp_ff.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, particles[W])
-        icp_ff.set_initial_mean(pb.R0, pb.t0)
-        icp_ff.stein_align()
+        scan_device(W, icp_ff)
     ph_ff = icp_ff.get_phase_times()
     icp_ff.close()
-    del os.environ["SVNICP_FILTER_FULL"]
     t_filter = ph_ff["filter_ms"] / max(ph_ff["iterations"], 1) * 1e-3
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    fp32_peak_results = 148 * 128 * sm_max * 1e6  # FP32 results/s: 128 lanes per SM (FFMA2 issues at half rate: scripts/micro/ffma2_bench.cu)
     roofline = dict(bound="hbm", kernel="k_filter + k_gn (correspondence + Gauss-Newton reduction pass, per iteration)",
                     achieved=b_alg / t_pass / 1e9, peak=hbm_peak, unit="GB/s", frac=b_alg / t_pass / 1e9 / hbm_peak, traffic=None,
                     peak_source=peak_src, algorithmic_bytes_per_launch=b_alg, ms_per_launch=t_pass * 1e3,
+                    note="the pass is FP32-issue bound for P >~ 20 (every loaded byte is reused by all particles: 0.57*P flop/B); the "
+                         "HBM-bound kernel of the path is k_filter alone (filter_only)",
                     filter_only=dict(achieved=16.0 * n_s * (1 + K) / t_filter / 1e9, frac=16.0 * n_s * (1 + K) / t_filter / 1e9 / hbm_peak,
                                      ms_per_launch=t_filter * 1e3,
-                                     note="k_filter streaming the K-slot table every iteration (SVNICP_FILTER_FULL=1 scan)"),
-                    fp32=dict(achieved_tflops=f_alg / t_pass / 1e12, peak_tflops=fp32_peak, frac=f_alg / t_pass / 1e12 / fp32_peak,
-                              note="brute-force-equivalent flops P*N_s*(130+8K); exact pruning skips most of them"))
+                                     note="k_filter streaming the K-slot table every iteration (SVNICP_FLAG_FILTER_FULL scan)"),
+                    gn_issue=dict(ms_per_launch=ph["gn_ms"] / iters, pairs_per_launch=float(P_g) * n_s,
+                                  ns_per_pair_per_sm_lane=ph["gn_ms"] / iters * 1e-3 * fp32_peak_results / (float(P_g) * n_s),
+                                  note="k_gn time expressed as FP32 issue slots per (particle, point) pair at 128 lanes/SM x sm_max; the executed "
+                                       "FP32 instruction count per pair is in profiles/ (ncu)"))
     # dram__bytes_{read,write}.sum per launch from the committed ncu --set full captures (profiles/), if present
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        roofline["traffic"] = tr["k_filter_bytes_per_launch"] + tr["k_gn_bytes_per_launch_late"]
-        roofline["traffic_detail"] = tr
-    except Exception:
-        pass
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", name)))
+            roofline["traffic"] = tr["k_filter_bytes_per_launch"] + tr["k_gn_bytes_per_launch_late"]
+            roofline["traffic_detail"] = tr
+            break
+        except Exception:  # noqa: BLE001
+            pass
 
     # secondary variants of the same scan: the reference's own pre-processing (uniform down-sampling
     # 0.5 m then 1.5 m voxels, OdometryPipeline.cpp:559-560) and reference-style early stop (geodeAlpha.yaml:9,17-19)
@@ -345,51 +451,52 @@ def main():
         ds = synth.uniform_downsample(synth.uniform_downsample(pb.source, 0.5), 1.5)
         ds_dev = torch.from_numpy(np.ascontiguousarray(ds)).to(dev)
 
-        def scan_ds(i):
-            icp.add_cloud_device(ds_dev.data_ptr(), len(ds), tgt_dev.data_ptr(), n_t, particles[i])
-            icp.set_initial_mean(pb.R0, pb.t0)
-            icp.stein_align()
-            return icp.get_transformation()
+        def run_variant(h, src_ptr, ns, parts, steps=args.steps):
+            def scan(i):
+                h.add_cloud_device(src_ptr, ns, tgt_dev.data_ptr(), n_t, parts[i % len(parts)])
+                h.set_initial_mean(pb.R0, pb.t0)
+                h.stein_align()
+                return h.get_transformation()
+            scan(0)
+            ms, mean = timed(scan, 1, steps)
+            return dict(scans_per_sec=steps / (ms * 1e-3), ms_per_scan=ms / steps, mean=[float(v) for v in mean])
 
-        scan_ds(0)
-        ms_ds, mean_ds = timed(scan_ds, 1, args.steps)
-        variants["downsampled_source"] = dict(n_s=int(len(ds)), scans_per_sec=args.steps / (ms_ds * 1e-3), ms_per_scan=ms_ds / args.steps,
-                                              mean=[float(v) for v in mean_ds])
+        variants["downsampled_source"] = dict(n_s=int(len(ds)), **run_variant(icp, ds_dev.data_ptr(), len(ds), particles))
         prm_es = sv.SteinICPParam(iterations=100, KNN_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"],
                                   SVN_full_grad=WORKLOAD["svn_full_grad"], check_early_stop=True, convergence_threshold=5e-4)
         icp_es = sv.SVNICP(prm_es, particles[0], device=local_rank)
         icp_es.set_stream(stream.cuda_stream)
-
-        def scan_es(i):
-            icp_es.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, particles[i])
-            icp_es.set_initial_mean(pb.R0, pb.t0)
-            icp_es.stein_align()
-            return icp_es.get_transformation()
-
-        scan_es(0)
-        ms_es, _ = timed(scan_es, 1, args.steps)
-        variants["early_stop_thr5e-4_max100"] = dict(scans_per_sec=args.steps / (ms_es * 1e-3), ms_per_scan=ms_es / args.steps,
-                                                     iterations_executed=icp_es.iterations_done())
+        variants["early_stop_thr5e-4_max100"] = run_variant(icp_es, src_dev.data_ptr(), n_s, particles)
+        variants["early_stop_thr5e-4_max100"]["iterations_executed"] = icp_es.iterations_done()
         icp_es.close()
+        # BASELINE.json configs[0]: 100 particles on the voxel-down-sampled scan (the reference's CPU-runnable case)
+        p100 = [synth.init_particles(100, rng) for _ in range(4)]
+        icp_c0 = sv.SVNICP(sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=WORKLOAD["max_dist"], lr=WORKLOAD["lr"],
+                                            SVN_full_grad=WORKLOAD["svn_full_grad"]), p100[0], device=local_rank)
+        icp_c0.set_stream(stream.cuda_stream)
+        variants["config0_p100_downsampled"] = dict(n_s=int(len(ds)), particles=100, **run_variant(icp_c0, ds_dev.data_ptr(), len(ds), p100))
+        variants["config0_p100_raw_scan"] = dict(n_s=n_s, particles=100, **run_variant(icp_c0, src_dev.data_ptr(), n_s, p100))
+        icp_c0.close()
+        # the shipped regime (geodeAlpha.yaml:9-22): 30 particles, <= 100 iterations, early stop 5e-4, pre-conditioned SVGD step
+        # (SVNFullGrad false), down-sampled source
+        p30 = [synth.init_particles(30, rng) for _ in range(4)]
+        icp_sh = sv.SVNICP(sv.SteinICPParam(iterations=100, KNN_count=K, max_dist=3.0, lr=1.0, SVN_full_grad=False, check_early_stop=True,
+                                            convergence_threshold=5e-4), p30[0], device=local_rank)
+        icp_sh.set_stream(stream.cuda_stream)
+        variants["shipped_p30_es_downsampled"] = dict(n_s=int(len(ds)), particles=30, **run_variant(icp_sh, ds_dev.data_ptr(), len(ds), p30))
+        variants["shipped_p30_es_downsampled"]["iterations_executed"] = icp_sh.iterations_done()
+        icp_sh.close()
         # the other registration class behind the same interface (class_type = SVGDICP): same scan,
         # same particle count, the reference's shipped SVGD settings (Adam, lr 0.03; stein_icp params)
         prm_gd = sv.SteinICPParam(iterations=I, KNN_count=K, max_dist=WORKLOAD["max_dist"], lr=0.03, optimizer="Adam", check_early_stop=False)
         icp_gd = sv.SVGDICP(prm_gd, particles[0], device=local_rank)
         icp_gd.set_stream(stream.cuda_stream)
-
-        def scan_gd(i):
-            icp_gd.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, particles[i])
-            icp_gd.set_initial_mean(pb.R0, pb.t0)
-            icp_gd.stein_align()
-            return icp_gd.get_transformation()
-
-        scan_gd(0)
-        ms_gd, mean_gd = timed(scan_gd, 1, args.steps)
+        variants["svgd_icp_class_adam"] = run_variant(icp_gd, src_dev.data_ptr(), n_s, particles, steps=min(args.steps, 5))
         icp_gd.set_profiling(True)
-        scan_gd(1)
-        ph_gd = icp_gd.get_phase_times()
-        variants["svgd_icp_class_adam"] = dict(scans_per_sec=args.steps / (ms_gd * 1e-3), ms_per_scan=ms_gd / args.steps,
-                                               phases_ms_per_scan=ph_gd, mean=[float(v) for v in mean_gd])
+        icp_gd.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, particles[1])
+        icp_gd.set_initial_mean(pb.R0, pb.t0)
+        icp_gd.stein_align()
+        variants["svgd_icp_class_adam"]["phases_ms_per_scan"] = icp_gd.get_phase_times()
         icp_gd.close()
 
     # The reference ITSELF on this GPU: its unmodified SVNICP sources + its vendored knn.cu against
@@ -423,24 +530,36 @@ def main():
         else:
             reference_on_gpu = dict(ok=False, error="oracle/_ref/libsvnicp_ref_cuda.so not built (oracle/build_ref_cuda.sh needs /root/reference)")
 
+    # CPU baseline (rank 0, N = 1 only): needs the candidate table for the full-size iteration -> one tiny parity-tap handle
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        tap = sv.SVNICP(sv.SteinICPParam(iterations=0, KNN_count=K, max_dist=WORKLOAD["max_dist"], debug_corr=True), np.zeros((6, 1)), device=local_rank)
+        tap.add_cloud_device(src_dev.data_ptr(), n_s, tgt_dev.data_ptr(), n_t, np.zeros((6, 1)))
+        tap.set_initial_mean(pb.R0, pb.t0)
+        tap.stein_align()
+        cand_idx = tap.get_candidates().astype(np.int64)
+        tap.close()
+        cpu_baseline = cpu_baseline_port(pb, cand_idx)
+        if not args.no_variants:
+            cpu_baseline["config0_full_measurement"] = cpu_config0("port")
+
     if rank == 0:
         h2d = (n_s + n_t) * 24 + 6 * P * 8
         d2h = (48 + 6 * P) * 8
         line = dict(metric=METRIC, value=args.steps / (ms_dev * 1e-3), unit="scans/sec", n_gpus=world, steps=args.steps, warmup=W,
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32 geometry / f64 reduction+Stein",
-                    data="synthetic",
-                    config=dict(workload=workload_name, n_s=n_s, n_t=n_t,
-                                l2="candidate table 16*N_s*K bytes > 126 MB L2 is re-streamed every iteration; inputs are not L2 resident",
-                                particles_per_gpu=P_g, **WORKLOAD),
+                    data="synthetic", config=bench_config(n_s, n_t, world),
                     e2e=dict(value=args.steps / (ms_e2e * 1e-3), unit="scans/sec", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=int(launches), roofline=roofline, clocks=clocks,
                     phases_ms_per_scan=ph, scan_info=info, prune_mean_kept=[round(float(x), 2) for x in prune], variants=variants,
-                    check=dict(mean=[float(v) for v in out[0]], gt=[float(v) for v in pb.gt_rel]), datagen_s=gen_s)
+                    check=check, datagen_s=gen_s)
         if reference_on_gpu is not None:
             line["reference_on_gpu"] = reference_on_gpu
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_port(pb)
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
+        if world > 1 and not check["sharded_vs_single_max_abs"]["ok"]:
+            raise SystemExit(f"sharded run differs from the single-GPU run: {check['sharded_vs_single_max_abs']}")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

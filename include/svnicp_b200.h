@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SVNICP_B200_ABI_VERSION 1
+#define SVNICP_B200_ABI_VERSION 2
 
 typedef struct svnicp_handle_t *svnicp_handle;
 
@@ -71,7 +71,18 @@ typedef struct {
   double grid_cell;              /* candidate-builder voxel-hash cell edge in metres (0 -> 1.5) */
   int32_t debug_corr;            /* 1 -> keep per-(particle,point) correspondences of the LAST executed
                                     iteration for svnicp_get_correspondences (parity tests)    */
+  int32_t flags;                 /* SVNICP_FLAG_* bit mask, read once by svnicp_create (A/B measurements; 0 = the
+                                    measured-best default path)                                  */
+  int32_t gn_stages;             /* TMA pipeline depth of the Gauss-Newton kernel (0 -> 3)      */
+  int32_t gn_smem_kb;            /* shared-memory budget of one Gauss-Newton CTA in KiB (0 -> 100) */
 } svnicp_params;
+
+/* svnicp_params.flags (all default off; none changes a result beyond the documented summation-order effects) */
+#define SVNICP_FLAG_NO_PARTICLE_SORT 1  /* keep the caller's particle order internally (no pose-space ordering)      */
+#define SVNICP_FLAG_FILTER_FULL 2       /* prune from the full K-slot candidate table every iteration (no list reuse) */
+#define SVNICP_FLAG_SPLIT_TAIL 4        /* Stein phase as separate kernels (decide, 5 median passes, Stein, update)   */
+#define SVNICP_FLAG_NCCL_GATHER 8       /* sharded: ncclAllGather per iteration instead of the peer-memory exchange    */
+#define SVNICP_FLAG_REUSE_STATS 16      /* svnicp_get_prune_stats reports the fraction of rows served by list reuse    */
 
 /* Fill with the defaults of SteinICPParam (SVGDICP.h:41-57). */
 void svnicp_default_params(svnicp_params *p);
@@ -145,7 +156,7 @@ int svnicp_get_gn_system(svnicp_handle h, double *out_H, double *out_b, double *
 /* Stein step of the last executed iteration, local slice: delta [P_local][6]; bandwidth h. */
 int svnicp_get_stein(svnicp_handle h, double *out_delta, double *out_bandwidth);
 /* mean candidates per (point) kept by the exact pruning pass, per iteration [iterations]
- * (with SVNICP_DEBUG_REUSE set in the environment: the fraction of rows pruned from the previous iteration's list) */
+ * (handle created with SVNICP_FLAG_REUSE_STATS: the fraction of rows pruned from the previous iteration's list) */
 int svnicp_get_prune_stats(svnicp_handle h, double *out_mean_kept, int32_t *rows);
 /* device time of the phases of the last scan in ms: {setup, iterations, epilogue, total} */
 int svnicp_get_timing(svnicp_handle h, double out4[4]);

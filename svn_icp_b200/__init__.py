@@ -34,7 +34,16 @@ class _CParams(C.Structure):
                 ("max_dist", C.c_double), ("normalize_cloud", C.c_int32), ("optimizer", C.c_char * 16),
                 ("check_early_stop", C.c_int32), ("convergence_steps", C.c_int32), ("convergence_threshold", C.c_double),
                 ("KNN_count", C.c_int32), ("SVN_full_grad", C.c_int32), ("use_weight_mean", C.c_int32),
-                ("grid_cell", C.c_double), ("debug_corr", C.c_int32)]
+                ("grid_cell", C.c_double), ("debug_corr", C.c_int32), ("flags", C.c_int32), ("gn_stages", C.c_int32),
+                ("gn_smem_kb", C.c_int32)]
+
+
+# svnicp_params.flags (include/svnicp_b200.h): A/B switches read once at construction
+FLAG_NO_PARTICLE_SORT = 1
+FLAG_FILTER_FULL = 2
+FLAG_SPLIT_TAIL = 4
+FLAG_NCCL_GATHER = 8
+FLAG_REUSE_STATS = 16
 
 
 @dataclasses.dataclass
@@ -55,6 +64,9 @@ class SteinICPParam:
     # extensions
     grid_cell: float = 0.0
     debug_corr: bool = False
+    flags: int = 0
+    gn_stages: int = 0
+    gn_smem_kb: int = 0
 
 
 @dataclasses.dataclass
@@ -107,8 +119,34 @@ def load_library() -> C.CDLL:
         lib.svnicp_map_last_error.restype = C.c_char_p
         lib.svnicp_map_last_error.argtypes = [C.c_void_p]
         lib.svnicp_default_params.restype = None
+        V, I, L, D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+        for name, at in _ARGTYPES(V, I, L, D).items():
+            getattr(lib, name).argtypes = at
         _lib = lib
     return _lib
+
+
+def _ARGTYPES(V, I, L, D):
+    """argtypes of every export of include/svnicp_b200.h (pointers as void*): ctypes then converts Python ints itself and
+    rejects a wrong argument count instead of passing garbage."""
+    return {
+        "svnicp_abi_version": [], "svnicp_default_params": [V], "svnicp_create": [V, V, I, V, I, I], "svnicp_set_stream": [V, V],
+        "svnicp_nccl_unique_id": [V], "svnicp_init_sharding": [V, V, I, I], "svnicp_add_cloud": [V, V, L, I, V, L, I, V],
+        "svnicp_set_initial_mean": [V, V, V], "svnicp_align": [V], "svnicp_get_transformation": [V, V],
+        "svnicp_get_distribution": [V, V], "svnicp_get_cov_matrix": [V, V], "svnicp_get_particles": [V, V],
+        "svnicp_get_particle_weight": [V, V], "svnicp_get_particle_history": [V, V, V], "svnicp_get_runtime": [V, V],
+        "svnicp_set_k": [V, I], "svnicp_set_threshold": [V, D], "svnicp_initialize_particles": [I, V, V, C.c_uint64, V],
+        "svnicp_initialize_particles_gaussian": [I, V, C.c_uint64, V], "svnicp_iterations_done": [V, V],
+        "svnicp_get_candidates": [V, V, V], "svnicp_get_source_f32": [V, V], "svnicp_get_correspondences": [V, V, V, V],
+        "svnicp_get_gn_system": [V, V, V, V], "svnicp_get_stein": [V, V, V], "svnicp_get_prune_stats": [V, V, V],
+        "svnicp_get_timing": [V, V], "svnicp_get_slice": [V, V, V], "svnicp_get_launch_count": [V, V],
+        "svnicp_set_profiling": [V, I], "svnicp_get_phase_times": [V, V], "svnicp_get_scan_info": [V, V],
+        "svnicp_get_tail_stamps": [V, V],
+        "svnicp_map_create": [V, D, D, I, L, I], "svnicp_map_clear": [V], "svnicp_map_add_cloud": [V, V, L, I, I, V, V],
+        "svnicp_map_get": [V, V, D, V, V], "svnicp_map_download": [V, V, L], "svnicp_map_size": [V, V, V],
+        "svnicp_pre_create": [V, L, I], "svnicp_pre_crop": [V, V, L, I, D, D, V, V, V],
+        "svnicp_pre_downsample_uniform": [V, V, L, I, D, V, V], "svnicp_pre_to_f64": [V, V, L, V], "svnicp_pre_download": [V, V, L, V],
+    }
 
 
 def _p(a):
@@ -158,7 +196,7 @@ class SVNICP:
         self.param = dataclasses.replace(param)
         cp = _CParams()
         self._lib.svnicp_default_params(C.byref(cp))
-        for f in ("iterations", "batch_size", "convergence_steps", "KNN_count"):
+        for f in ("iterations", "batch_size", "convergence_steps", "KNN_count", "flags", "gn_stages", "gn_smem_kb"):
             setattr(cp, f, int(getattr(param, f)))
         for f in ("use_minibatch", "normalize_cloud", "check_early_stop", "SVN_full_grad", "debug_corr"):
             setattr(cp, f, int(bool(getattr(param, f))))
@@ -197,12 +235,17 @@ class SVNICP:
         self._check(self._lib.svnicp_init_sharding(self._h, C.c_char_p(unique_id), C.c_int(rank), C.c_int(n_ranks)), "init_sharding")
 
     # -- the reference interface ------------------------------------------------------------------
-    def add_cloud(self, source, target, init_pose):
-        """SVGDICP::add_cloud (SVGDICP.cpp:46-62).  source/target: host arrays [N,3] float64."""
-        source, target = _f64(source), _f64(target)
+    def _init_pose(self, init_pose):
+        """[6, P] float64, P checked: the C side reads exactly 6*P doubles (the count is fixed at construction, SVNICP.cpp:42,167)."""
         init_pose = _f64(init_pose).reshape(6, -1)
         if init_pose.shape[1] != self.particle_size:
             raise SvnIcpError("add_cloud: particle count is fixed at construction (SVNICP.cpp:42,167)")
+        return init_pose
+
+    def add_cloud(self, source, target, init_pose):
+        """SVGDICP::add_cloud (SVGDICP.cpp:46-62).  source/target: host arrays [N,3] float64."""
+        source, target = _f64(source), _f64(target)
+        init_pose = self._init_pose(init_pose)
         self.n_s = len(source)
         self._check(self._lib.svnicp_add_cloud(self._h, _p(source), C.c_int64(len(source)), C.c_int(0), _p(target),
                                                C.c_int64(len(target)), C.c_int(0), _p(init_pose)), "add_cloud")
@@ -210,14 +253,14 @@ class SVNICP:
     def add_cloud_device(self, source_ptr: int, n_s: int, target_ptr: int, n_t: int, init_pose):
         """Same, with the clouds already resident in HBM (float64 [N,3] device pointers), as in the reference where
         the caller uploads (OdometryPipeline.cpp:574,581)."""
-        init_pose = _f64(init_pose).reshape(6, -1)
+        init_pose = self._init_pose(init_pose)
         self.n_s = n_s
         self._check(self._lib.svnicp_add_cloud(self._h, C.c_void_p(source_ptr), C.c_int64(n_s), C.c_int(1), C.c_void_p(target_ptr),
                                                C.c_int64(n_t), C.c_int(1), _p(init_pose)), "add_cloud")
 
     def add_cloud_pinned(self, source_ptr: int, n_s: int, target_ptr: int, n_t: int, init_pose):
         """Same, host pointers given as integers (e.g. pinned torch tensors' data_ptr())."""
-        init_pose = _f64(init_pose).reshape(6, -1)
+        init_pose = self._init_pose(init_pose)
         self.n_s = n_s
         self._check(self._lib.svnicp_add_cloud(self._h, C.c_void_p(source_ptr), C.c_int64(n_s), C.c_int(0), C.c_void_p(target_ptr),
                                                C.c_int64(n_t), C.c_int(0), _p(init_pose)), "add_cloud")

@@ -441,7 +441,7 @@ k_knn(const double *__restrict__ q0, int row_lo, int row_hi, const double *__res
       const double nrm = sqrt((double)cx * cx + (double)cy * cy + (double)cz * cz);
       const float w = (k < count) ? __double2float_rd(nrm * (1.0 - 1e-6)) : INFINITY;  // padded duplicates never need a visit
       cand[(size_t)b * K + k] = make_float4(cx, cy, cz, w);
-      cand_idx[(size_t)b * K + k] = gi;
+      if (cand_idx) cand_idx[(size_t)b * K + k] = gi;  // parity taps only (debug_corr)
     }
     __syncwarp();
   }

@@ -87,7 +87,7 @@ struct svnicp_handle_t {
   // scan inputs
   int64_t n_s = 0, n_t = 0;
   int n_pad = 0;
-  bool have_cloud = false, aligned = false;
+  bool have_cloud = false, aligned = false, shape_dirty = false;
   ScanConst sc;
   // device buffers
   DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, rec, xs, delta, Hbar_inv, stats, particles, init_pose, prep_scratch_d;
@@ -95,7 +95,7 @@ struct svnicp_handle_t {
   // SVGD-ICP class state (class_type = SVGDICP): parameters, pose_particles_ carried between scans, optimizer moments
   DevBuf<double> pose6, prev, opt_state;
   int optimizer = -1;
-  DevBuf<float4> sp, cand, clist, spair;
+  DevBuf<float4> sp, cand, clist;
   // list reuse across iterations (k_filter): second list buffer, true list lengths and the balls the lists are exact for
   DevBuf<float4> clist2, ball[2];
   DevBuf<int> ccount2, cbase[2];
@@ -104,7 +104,6 @@ struct svnicp_handle_t {
   std::vector<int> perm;
   std::vector<double> perm_stage;
   bool permuted = false;
-  int pair_mode = 0;
   int rows_per_rank = 0;
   DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc, cand_idx;
   int Kp = 100;  // misc: [0] cursor, [1] fallback count
@@ -185,6 +184,9 @@ void svnicp_default_params(svnicp_params *p) {
   p->use_weight_mean = 0;
   p->grid_cell = 0.0;
   p->debug_corr = 0;
+  p->flags = 0;
+  p->gn_stages = 0;
+  p->gn_smem_kb = 0;
 }
 
 const char *svnicp_last_error(svnicp_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -210,7 +212,7 @@ static SvgdArgs svgd_args(svnicp_handle h) {
 // exit is a WARP vote: 32 particles that sit close together in pose space agree earlier, and a rank whose slice is a compact
 // cluster gets a smaller pruning ball.  So the particles are laid out in Morton order of (x, y, yaw) quantised to 3 bits
 // each (measured at configs[1]: k_gn 30.7 -> 28.4 ms per scan); every getter maps back to the caller's order.  The Stein step
-// sums over all particles either way; only the order of its fp64 sums changes.  SVNICP_NO_PARTICLE_SORT=1 keeps the
+// sums over all particles either way; only the order of its fp64 sums changes.  SVNICP_FLAG_NO_PARTICLE_SORT keeps the
 // caller's order (A/B measurements).  Not applied to the SVGD-ICP class (its pose_particles_ state spans scans).
 static void compute_particle_order(svnicp_handle h, const double *init_pose) {
   const int P = h->P;
@@ -221,7 +223,7 @@ static void compute_particle_order(svnicp_handle h, const double *init_pose) {
   // it had before.  Measured on 8 GPUs at configs[1] with the order applied ACROSS ranks instead: each slice becomes a compact
   // cluster (kept candidates 72 -> 47, k_gn 4.34 -> 3.94 ms per scan) but the clusters differ in cost and the wait at the
   // per-iteration all-gather grows from 0.9 to 2.2 ms: 95.6 -> 90.5 scans/s.
-  if (!init_pose || P < 64 || h->class_type != SVNICP_CLASS_SVNICP || getenv("SVNICP_NO_PARTICLE_SORT")) return;
+  if (!init_pose || P < 64 || h->class_type != SVNICP_CLASS_SVNICP || (h->prm.flags & SVNICP_FLAG_NO_PARTICLE_SORT)) return;
   const int comps[3] = {0, 1, 5};
   std::vector<int> code(P, 0);
   for (int blk = 0; blk < h->n_ranks; blk++) {  // identical on every rank: depends on init_pose and the slice bounds only
@@ -344,7 +346,6 @@ int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_
     h->stream = h->own_stream;
     for (int i = 0; i < 4; i++) CU(cudaEventCreate(&h->ev[i]));
     init_iter_kernels();
-    init_pair_kernels();
     CU(cudaGetLastError());
     int r = alloc_particle_state(h);
     if (r) return r;
@@ -381,7 +382,7 @@ void svnicp_destroy(svnicp_handle h) {
                          &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose, &h->prep_scratch_d, &h->pose6, &h->prev, &h->opt_state};
   h->prep_scratch_i.release();
   for (auto *b : d) b->release();
-  h->sp.release(); h->cand.release(); h->clist.release(); h->spair.release();
+  h->sp.release(); h->cand.release(); h->clist.release();
   h->clist2.release(); h->ccount2.release();
   for (int i = 0; i < 2; i++) { h->ball[i].release(); h->cbase[i].release(); }
   h->cand_idx.release();
@@ -450,16 +451,10 @@ static int choose_shape(svnicp_handle h) {
   int TB = 32;
   int S = 3;
   size_t budget = 100 * 1024;  // two CTAs of k_gn per SM (registers allow no more: measured)
-  if (const char *e = getenv("SVNICP_GN_STAGES")) S = atoi(e) > 1 ? atoi(e) : 2;          // tuning knobs (bench sweeps)
-  if (const char *e = getenv("SVNICP_GN_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
-  // Default: the scalar kernel (256 consumers, two CTAs per SM).  SVNICP_GN_PAIR=1 selects the packed-fp32x2 pair mode
-  // (gn_pair.cu, 512 threads, one CTA per SM; needs >= 32 local particles so a warp shares a source point).  Measured at
-  // configs[1]: pair mode issues 33 % fewer instructions but is not faster (32.7 vs 30.6 ms of k_gn per scan) because
-  // FFMA2 delivers the same 32 results/clk/SMSP as scalar FFMA (scripts/micro/ffma2_bench.cu) -- see DESIGN.md.
-  h->pair_mode = (h->P_l >= 32 && getenv("SVNICP_GN_PAIR") && h->class_type == SVNICP_CLASS_SVNICP) ? 1 : 0;
-  const int consumers = h->pair_mode ? 512 : 256;
-  if (h->pair_mode && !getenv("SVNICP_GN_SMEM_KB")) budget = 160 * 1024;
-  while (TB > (h->pair_mode ? 8 : 4) && gn_stage_bytes(TB, Kp) * S > budget) TB >>= 1;
+  if (h->prm.gn_stages > 1) S = h->prm.gn_stages;  // tuning knobs (svnicp_params extensions, bench sweeps)
+  if (h->prm.gn_smem_kb > 0) budget = (size_t)h->prm.gn_smem_kb * 1024;
+  const int consumers = 256;
+  while (TB > 4 && gn_stage_bytes(TB, Kp) * S > budget) TB >>= 1;
   h->TB = TB;
   h->stages = S;
   h->gn_smem = gn_stage_bytes(TB, Kp) * S + 2 * S * sizeof(uint64_t) + 128;
@@ -472,34 +467,27 @@ static int choose_shape(svnicp_handle h) {
   return SVNICP_OK;
 }
 
-int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int source_on_device, const double *target, int64_t n_t,
-                     int target_on_device, const double *init_pose) {
-  if (!h) return SVNICP_ERR_INVALID;
-  if (!source || !target || n_s < 1 || n_t < 1) return fail(h, SVNICP_ERR_INVALID, "add_cloud: empty cloud (n_s=%lld, n_t=%lld)", (long long)n_s, (long long)n_t);
-  if (n_s > (1ll << 30) || n_t > (1ll << 30)) return fail(h, SVNICP_ERR_INVALID, "add_cloud: cloud too large");
-  CU(cudaSetDevice(h->device));
+// Everything whose size depends on (n_s, n_t, K, P_l): launch shape of the Gauss-Newton kernel, candidate table, pruned lists,
+// voxel hash of the map.  Runs at add_cloud, and again at the head of stein_align when set_k changed K in between
+// (SVGDICP.h:98: K_source_ takes effect at the next stein_align; the stored clouds stay valid).
+static int prepare_scan(svnicp_handle h) {
+  const int64_t n_s = h->n_s, n_t = h->n_t;
   choose_shape(h);
   const int TB = h->TB;
   const int n_pad = (int)(((n_s + TB - 1) / TB) * TB);
-  CU(h->src64.ensure((size_t)3 * n_s));
-  CU(h->tgt64.ensure((size_t)3 * n_t));
-  CU(cudaMemcpyAsync(h->src64.p, source, (size_t)3 * n_s * sizeof(double), source_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->tgt64.p, target, (size_t)3 * n_t * sizeof(double), target_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-  h->n_s = n_s;
-  h->n_t = n_t;
   h->n_pad = n_pad;
   CU(h->q0.ensure((size_t)3 * n_s));
   CU(h->sp.ensure((size_t)n_pad + 64));
-  CU(h->spair.ensure((size_t)n_pad + 64));
   // candidate rows are built sharded across the ranks and all-gathered once per scan: n_ranks blocks of rows_per_rank rows
   h->rows_per_rank = (int)((n_s + h->n_ranks - 1) / h->n_ranks);
   CU(h->cand.ensure((size_t)h->rows_per_rank * h->n_ranks * h->K));
-  CU(h->cand_idx.ensure((size_t)h->rows_per_rank * h->n_ranks * h->K));
+  // global map index per slot: only the parity taps read it (svnicp_get_candidates / _get_correspondences)
+  if (h->prm.debug_corr) CU(h->cand_idx.ensure((size_t)h->rows_per_rank * h->n_ranks * h->K));
   CU(h->clist.ensure((size_t)n_pad * h->Kp));
   CU(h->ccount.ensure((size_t)n_pad + 64));
   CU(cudaMemsetAsync(h->ccount.p, 0, ((size_t)n_pad + 64) * sizeof(int), h->stream));
-  // SVNICP_FILTER_FULL=1: prune from the full K-slot table every iteration (A/B measurements, roofline of the streaming pass)
-  h->filter_reuse = (!h->pair_mode && getenv("SVNICP_FILTER_FULL") == nullptr) ? 1 : 0;
+  // SVNICP_FLAG_FILTER_FULL: prune from the full K-slot table every iteration (A/B measurements, roofline of the streaming pass)
+  h->filter_reuse = (h->prm.flags & SVNICP_FLAG_FILTER_FULL) ? 0 : 1;
   if (h->filter_reuse) {
     CU(h->clist2.ensure((size_t)n_pad * h->Kp));
     CU(h->ccount2.ensure((size_t)n_pad + 64));
@@ -519,7 +507,7 @@ int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int sou
   CU(h->sidx.ensure((size_t)n_t));
   CU(h->sxyz.ensure((size_t)3 * n_t));
   const int n_tiles = n_pad / TB;
-  int n_slices = ((h->pair_mode ? 1 : 2) * h->sm_count) / h->n_pgroups;
+  int n_slices = (2 * h->sm_count) / h->n_pgroups;
   if (n_slices < 1) n_slices = 1;
   if (n_slices > n_tiles) n_slices = n_tiles;
   h->n_slices = n_slices;
@@ -528,6 +516,24 @@ int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int sou
     CU(h->dbg_idx.ensure((size_t)h->P_l * n_s));
     CU(h->dbg_mask.ensure((size_t)h->P_l * n_s));
   }
+  h->shape_dirty = false;
+  return SVNICP_OK;
+}
+
+int svnicp_add_cloud(svnicp_handle h, const double *source, int64_t n_s, int source_on_device, const double *target, int64_t n_t,
+                     int target_on_device, const double *init_pose) {
+  if (!h) return SVNICP_ERR_INVALID;
+  if (!source || !target || n_s < 1 || n_t < 1) return fail(h, SVNICP_ERR_INVALID, "add_cloud: empty cloud (n_s=%lld, n_t=%lld)", (long long)n_s, (long long)n_t);
+  if (n_s > (1ll << 30) || n_t > (1ll << 30)) return fail(h, SVNICP_ERR_INVALID, "add_cloud: cloud too large");
+  CU(cudaSetDevice(h->device));
+  CU(h->src64.ensure((size_t)3 * n_s));
+  CU(h->tgt64.ensure((size_t)3 * n_t));
+  CU(cudaMemcpyAsync(h->src64.p, source, (size_t)3 * n_s * sizeof(double), source_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->tgt64.p, target, (size_t)3 * n_t * sizeof(double), target_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  h->n_s = n_s;
+  h->n_t = n_t;
+  const int rc = prepare_scan(h);
+  if (rc) return rc;
   h->have_cloud = true;
   h->aligned = false;
   return upload_particles(h, init_pose);  // SVGDICP.cpp:47-61 (also synchronises the cloud copies)
@@ -543,8 +549,8 @@ int svnicp_set_initial_mean(svnicp_handle h, const double R0[9], const double t0
 int svnicp_set_k(svnicp_handle h, int k) {
   if (!h) return SVNICP_ERR_INVALID;
   if (k < 1 || k > 256) return fail(h, SVNICP_ERR_INVALID, "set_k: K must be in [1,256]");
-  h->K = k;            // SVGDICP.h:98; takes effect at the next add_cloud (buffers are sized there)
-  h->have_cloud = false;
+  if (k != h->K) h->shape_dirty = true;  // SVGDICP.h:98: K_source_ takes effect at the next stein_align; the stored clouds stay
+  h->K = k;
   return SVNICP_OK;
 }
 
@@ -568,6 +574,10 @@ int svnicp_align(svnicp_handle h) {
   cudaStream_t st = h->stream;
   const int I = h->prm.iterations;
   h->launches = 0;
+  if (h->shape_dirty) {
+    const int rc = prepare_scan(h);
+    if (rc) return rc;
+  }
   // host mirrors sized for this run
   if (h->h_hist_cap < (size_t)(I > 0 ? I : 1) * 6 * h->P) {
     if (h->h_history) cudaFreeHost(h->h_history);
@@ -592,6 +602,9 @@ int svnicp_align(svnicp_handle h) {
   CU(cudaMemsetAsync(h->kept_hist.p, 0, ((size_t)I + 2) * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(h->misc.p, 0, 8 * sizeof(int), st));
   const bool svgd = h->class_type == SVNICP_CLASS_SVGDICP;
+  // A scan may be run again without a fresh add_cloud (the reference keeps R_/t_ and rewrites history rows 0..I-1; SVGDICP
+  // rebuilds its optimizer in every stein_align, SVGDICP.cpp:73): restart the device-side iteration state, keep the poses.
+  h->launches += launch_align_reset(h->ctrl.p, svgd ? h->opt_state.p : nullptr, svgd ? (size_t)12 * h->P_l : 0, st);
   const SvgdArgs sv = svgd ? svgd_args(h) : SvgdArgs();
   if (svgd && h->optimizer < 0) {
     // SVGDICP.cpp:73-75: "No optimizer chosen" -> NO_OPTIMIZER before anything moves; the getters then describe the
@@ -627,7 +640,7 @@ int svnicp_align(svnicp_handle h) {
   size_t table = 1024;
   while (table < (size_t)2 * h->n_t) table <<= 1;
   cb.table_size = (int)table;
-  cb.sxyz = h->sxyz.p; cb.sidx = h->sidx.p; cb.cand = h->cand.p; cb.cand_idx = h->cand_idx.p;
+  cb.sxyz = h->sxyz.p; cb.sidx = h->sidx.p; cb.cand = h->cand.p; cb.cand_idx = h->prm.debug_corr ? h->cand_idx.p : nullptr;
   cb.sm_count = h->sm_count;
   cb.row_lo = h->rank * h->rows_per_rank;
   cb.row_hi = cb.row_lo + h->rows_per_rank < (int)h->n_s ? cb.row_lo + h->rows_per_rank : (int)h->n_s;
@@ -641,18 +654,16 @@ int svnicp_align(svnicp_handle h) {
     // the global map indices only feed the parity taps (svnicp_get_candidates / _get_correspondences): 20 % of the volume
     if (h->prm.debug_corr) NC(g_nccl.AllGather(h->cand_idx.p + (size_t)h->rank * blk, h->cand_idx.p, blk, ncclInt32, h->comm, st));
   }
-  if (h->pair_mode) h->launches += launch_spair(h->sp.p, h->spair.p, h->n_pad, st);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev[1], st));
 
   IterArgs ia;
   memset(&ia, 0, sizeof(ia));
-  ia.n_s = (int)h->n_s; ia.n_pad = h->n_pad; ia.K = h->K; ia.Kp = h->Kp; ia.cand_idx = h->cand_idx.p;
+  ia.n_s = (int)h->n_s; ia.n_pad = h->n_pad; ia.K = h->K; ia.Kp = h->Kp; ia.cand_idx = h->prm.debug_corr ? h->cand_idx.p : nullptr;
   ia.P = h->P; ia.p_lo = h->p_lo; ia.P_l = h->P_l;
   ia.sc = h->sc;
   ia.max_dist = (float)h->max_dist;
   ia.sp = h->sp.p; ia.cand = h->cand.p; ia.clist = h->clist.p; ia.ccount = h->ccount.p;
-  ia.spair = h->spair.p; ia.pair_mode = h->pair_mode;
   ia.R = h->R.p; ia.t = h->t.p; ia.xf = h->xf.p; ia.dnorm = h->dnorm.p; ia.part = h->part.p; ia.rec = h->rec.p; ia.ctrl = h->ctrl.p;
   ia.TB = h->TB; ia.stages = h->stages; ia.n_slices = h->n_slices; ia.n_pgroups = h->n_pgroups; ia.PG = h->PG; ia.RG = h->RG;
   ia.gn_smem = h->gn_smem; ia.sm_count = h->sm_count; ia.svn_full_grad = h->prm.SVN_full_grad;
@@ -672,8 +683,8 @@ int svnicp_align(svnicp_handle h) {
   sa.prep_scratch_d = h->prep_scratch_d.p;
   sa.prep_scratch_i = h->prep_scratch_i.p;
   // one cooperative kernel per iteration for decide + median + Stein + update + next prep (tail_fused.cu);
-  // SVNICP_NO_FUSED_TAIL=1 keeps the nine separate launches (A/B measurements, same-bits test)
-  const bool fused_tail = !svgd && getenv("SVNICP_NO_FUSED_TAIL") == nullptr;
+  // SVNICP_FLAG_SPLIT_TAIL keeps the nine separate launches (A/B measurements, same-bits test)
+  const bool fused_tail = !svgd && !(h->prm.flags & SVNICP_FLAG_SPLIT_TAIL);
 
   if (h->profile)
     while (h->prof_events.size() < (size_t)I * 7) {
@@ -705,9 +716,9 @@ int svnicp_align(svnicp_handle h) {
       ia.ball_prev = h->ball[cur ^ 1].p;
       ia.kept_hist = h->kept_hist.p;
     }
-    h->launches += h->pair_mode ? launch_filter_pair(ia, st) : launch_filter(ia, st);
+    h->launches += launch_filter(ia, st);
     PROF(2);
-    h->launches += h->pair_mode ? launch_gn_pair(ia, st) : launch_gn(ia, st);
+    h->launches += launch_gn(ia, st);
     if (h->prm.debug_corr) {  // parity tap: the transforms this iteration's correspondences were computed with
       CU(h->dbg_xf.ensure((size_t)(h->P_l > 0 ? h->P_l : 1) * 12));
       CU(cudaMemcpyAsync(h->dbg_xf.p, h->xf.p, (size_t)h->P_l * 12 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -782,27 +793,28 @@ int svnicp_align(svnicp_handle h) {
   return SVNICP_ALIGN_SUCCESS;
 }
 
-#define NEED_ALIGNED()                                                                 \
+#define NEED_ALIGNED(out)                                                              \
   if (!h) return SVNICP_ERR_INVALID;                                                   \
+  if (!(out)) return fail(h, SVNICP_ERR_INVALID, "null output pointer");               \
   if (!h->aligned) return fail(h, SVNICP_ERR_INVALID, "no result yet: call svnicp_align first");
 
 int svnicp_get_transformation(svnicp_handle h, double out6[6]) {
-  NEED_ALIGNED();
+  NEED_ALIGNED(out6);
   memcpy(out6, h->h_stats, 6 * sizeof(double));
   return SVNICP_OK;
 }
 int svnicp_get_distribution(svnicp_handle h, double out6[6]) {
-  NEED_ALIGNED();
+  NEED_ALIGNED(out6);
   memcpy(out6, h->h_stats + 6, 6 * sizeof(double));
   return SVNICP_OK;
 }
 int svnicp_get_cov_matrix(svnicp_handle h, double out36[36]) {
-  NEED_ALIGNED();
+  NEED_ALIGNED(out36);
   memcpy(out36, h->h_stats + 12, 36 * sizeof(double));
   return SVNICP_OK;
 }
 int svnicp_get_particles(svnicp_handle h, double *out) {
-  NEED_ALIGNED();
+  NEED_ALIGNED(out);
   if (!h->permuted) {
     memcpy(out, h->h_particles, (size_t)6 * h->P * sizeof(double));
   } else {  // back to the caller's particle order
@@ -813,6 +825,7 @@ int svnicp_get_particles(svnicp_handle h, double *out) {
 }
 int svnicp_get_particle_weight(svnicp_handle h, double *out) {
   if (!h) return SVNICP_ERR_INVALID;
+  if (!out) return fail(h, SVNICP_ERR_INVALID, "null output pointer");
   // SVNICP.cpp:46 + :281-284: float32 weights widened to double; SVGDICP.cpp:522-524: a vector of ones
   const double w = h->class_type == SVNICP_CLASS_SVGDICP ? 1.0 : (double)(1.0f / (float)h->P);
   for (int p = 0; p < h->P; p++) out[p] = w;
@@ -838,7 +851,7 @@ int svnicp_get_particle_history(svnicp_handle h, float *out, int32_t *rows) {
   return SVNICP_OK;
 }
 int svnicp_get_runtime(svnicp_handle h, double out3[3]) {
-  if (!h) return SVNICP_ERR_INVALID;
+  if (!h || !out3) return SVNICP_ERR_INVALID;
   // SVGDICP.h:94-96 {knn_duration_, update_duration_, finish_iter_}; SVNICP never fills them (Q12) -- we do, from CUDA events.
   out3[0] = h->ms_setup * 1e-3;
   out3[1] = h->ms_iter * 1e-3;
@@ -887,8 +900,8 @@ int svnicp_iterations_done(svnicp_handle h, int32_t *out) {
 
 int svnicp_get_candidates(svnicp_handle h, int32_t *out_idx, float *out_rel) {
   if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
-  if (out_idx && h->n_ranks > 1 && !h->prm.debug_corr)
-    return fail(h, SVNICP_ERR_INVALID, "sharded handle created without debug_corr: the map-index table was not gathered");
+  if (out_idx && !h->prm.debug_corr)
+    return fail(h, SVNICP_ERR_INVALID, "handle created without debug_corr: the map-index table is only written for the parity taps");
   CU(cudaSetDevice(h->device));
   const size_t n = (size_t)h->n_s * h->K;
   if (out_idx) CU(cudaMemcpy(out_idx, h->cand_idx.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -974,14 +987,14 @@ int svnicp_get_prune_stats(svnicp_handle h, double *out_mean_kept, int32_t *rows
     for (int i = 0; i < I; i++) {
       const unsigned long long v = h->h_kept[i];
       const double den = (double)(h->n_s > 0 ? h->n_s : 1);
-      // SVNICP_DEBUG_REUSE=1: fraction of rows pruned from the previous list instead of mean kept candidates (tuning aid)
-      out_mean_kept[i] = getenv("SVNICP_DEBUG_REUSE") ? (double)(v >> 40) / den : (double)(v & ((1ull << 40) - 1ull)) / den;
+      // SVNICP_FLAG_REUSE_STATS: fraction of rows pruned from the previous list instead of mean kept candidates (tuning aid)
+      out_mean_kept[i] = (h->prm.flags & SVNICP_FLAG_REUSE_STATS) ? (double)(v >> 40) / den : (double)(v & ((1ull << 40) - 1ull)) / den;
     }
   return SVNICP_OK;
 }
 
 int svnicp_get_timing(svnicp_handle h, double out4[4]) {
-  if (!h) return SVNICP_ERR_INVALID;
+  if (!h || !out4) return SVNICP_ERR_INVALID;
   out4[0] = h->ms_setup; out4[1] = h->ms_iter; out4[2] = h->ms_epi; out4[3] = h->ms_total;
   return SVNICP_OK;
 }

@@ -40,8 +40,6 @@ struct IterArgs {
   float max_dist;
   // buffers
   const float4 *sp, *cand;
-  const float4 *spair;  // [n_pad/2][2] interleaved source pairs (pair mode)
-  int pair_mode;        // 1: clist/ccount hold the interleaved pair lists of gn_pair.cu
   float4 *clist;
   int *ccount;
   // list reuse (k_filter): the previous iteration's pruned lists, their true lengths and the ball (centre query, radius)
@@ -103,11 +101,6 @@ __device__ __forceinline__ void gn_sum_partials(const IterArgs &a, int l, double
 }
 #endif
 int launch_prep(const IterArgs &a, cudaStream_t st, int x_only);
-// packed fp32x2 "pair mode" (gn_pair.cu): two source points per thread step
-void init_pair_kernels();
-int launch_spair(const float4 *sp, float4 *spair, int n_pad, cudaStream_t st);
-int launch_filter_pair(const IterArgs &a, cudaStream_t st);
-int launch_gn_pair(const IterArgs &a, cudaStream_t st);
 int launch_filter(const IterArgs &a, cudaStream_t st);
 int launch_gn(const IterArgs &a, cudaStream_t st);
 int launch_finalize(const IterArgs &a, cudaStream_t st);
@@ -142,6 +135,8 @@ int launch_median(const SteinArgs &a, cudaStream_t st);
 int launch_stein(const SteinArgs &a, cudaStream_t st);
 int launch_update(const SteinArgs &a, cudaStream_t st);
 int launch_stats(const SteinArgs &a, cudaStream_t st);
+// restart of the device-side iteration state at the head of every stein_align (poses are kept)
+int launch_align_reset(Ctrl *ctrl, double *opt_state, size_t n_opt, cudaStream_t st);
 int launch_init_particles(double *R, double *t, const double *init_pose_dev, int P, double *dnorm, int p_lo, int P_l, Ctrl *ctrl,
                           cudaStream_t st);
 

@@ -37,6 +37,14 @@ __global__ void k_particles_init(double *R, double *t, const double *init_pose, 
   if (p >= p_lo && p < p_lo + P_l) dnorm[p - p_lo] = 0.0;
 }
 
+// k_align_reset: head of every stein_align.  A second scan without add_cloud continues from the current poses (as the
+// reference does) but with fresh iteration counters, stop flag and -- SVGD-ICP class -- optimizer moments (SVGDICP.cpp:73).
+__global__ void k_align_reset(Ctrl *ctrl, double *opt_state, size_t n_opt) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { ctrl->stop = 0; ctrl->iter = 0; ctrl->iters_done = 0; ctrl->kept_total = 0ull; }
+  for (size_t k = i; k < n_opt; k += (size_t)gridDim.x * blockDim.x) opt_state[k] = 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_decide: early-stop decision for the PREVIOUS iteration + its history row; builds the SoA copy of the gathered
 // record the Stein kernels read; resets the median select.  Runs after the all-gather, so every rank (and every CTA:
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(DECIDE_THREADS) k_decide(SteinArgs a, int epil
   __syncthreads();
   if (s_stop) return;  // break BEFORE the history row of that iteration (Q9)
   const int gtid = blockIdx.x * blockDim.x + tid, gn = gridDim.x * blockDim.x;
-  if (it > 0) {
+  if (it > 0 && it - 1 < a.I) {
     float *row = a.history + (size_t)(it - 1) * 6 * a.P;
     for (int i = gtid; i < 6 * a.P; i += gn) {
       const int comp = i / a.P, p = i % a.P;
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(DECIDE_THREADS) k_decide(SteinArgs a, int epil
   for (int i = gtid; i < MED_PASSES * MED_BINS; i += gn) a.hist[i] = 0u;
   if (gtid < MED_PASSES) c->med_ticket[gtid] = 0u;
   if (gtid == 0) {
-    if (a.kept_hist) a.kept_hist[it] = c->kept_total;
+    if (a.kept_hist && it <= a.I) a.kept_hist[it] = c->kept_total;
     c->sel_prefix[0] = 0ull;
     c->sel_rank[0] = ((unsigned long long)a.P * (unsigned long long)a.P - 1ull) / 2ull;  // lower median
   }
@@ -479,6 +487,11 @@ __global__ void __launch_bounds__(1024) k_stats(SteinArgs a) {
 // launchers
 // ---------------------------------------------------------------------------------------------
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int launch_align_reset(Ctrl *ctrl, double *opt_state, size_t n_opt, cudaStream_t st) {
+  k_align_reset<<<n_opt > 4096 ? 32 : 1, 256, 0, st>>>(ctrl, opt_state, n_opt);
+  return 1;
+}
 
 int launch_init_particles(double *R, double *t, const double *init_pose_dev, int P, double *dnorm, int p_lo, int P_l, Ctrl *ctrl,
                           cudaStream_t st) {

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
     }
     __syncthreads();
     if (s_flag[0]) return;  // every CTA takes the same decision from the same record: nobody waits at a barrier
-    if (it > 0) {
+    if (it > 0 && it - 1 < a.I) {
       float *row = a.history + (size_t)(it - 1) * 6 * P;
       for (int i = gtid; i < 6 * P; i += gn) {
         const int comp = i / P, p = i % P;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tail_fused(SteinArgs a, IterA
     }
     for (int i = gtid; i < MED_PASSES * MED_BINS; i += gn) a.hist[i] = 0u;
     for (int i = gtid; i < PRUNE_BINS + 3; i += gn) a.prep_scratch_i[i] = 0;
-    if (gtid == 0 && a.kept_hist) a.kept_hist[it] = c->kept_total;
+    if (gtid == 0 && a.kept_hist && it <= a.I) a.kept_hist[it] = c->kept_total;
   }
   TF_STAMP(1);
   grid.sync();

@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_defaults(lib):
-    assert lib.svnicp_abi_version() == 1
+    assert lib.svnicp_abi_version() == 2
     p = sv._CParams()
     lib.svnicp_default_params(C.byref(p))
     # SteinICPParam defaults, reference SVGDICP.h:41-57
@@ -41,8 +41,15 @@ def test_abi_version_and_defaults(lib):
     assert (p.lr, p.max_dist, p.convergence_threshold) == (0.02, 1.0, 1e-5)
     assert (p.use_minibatch, p.normalize_cloud, p.check_early_stop, p.SVN_full_grad) == (0, 1, 0, 1)
     assert p.optimizer == b"Adam"
+    assert (p.flags, p.gn_stages, p.gn_smem_kb, p.debug_corr) == (0, 0, 0, 0)  # extensions default off
     d = sv.SteinICPParam()
     assert (d.iterations, d.lr, d.max_dist, d.KNN_count, d.SVN_full_grad) == (50, 0.02, 1.0, 100, True)
+
+
+def test_every_export_has_argtypes(lib):
+    """ctypes must know every signature (a missing argtypes entry lets a Python int be truncated to 32 bits)."""
+    for n in declared_symbols():
+        assert getattr(lib, n).argtypes is not None, n
 
 
 def test_no_cpu_fallback(lib):

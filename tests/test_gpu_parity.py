@@ -47,7 +47,7 @@ def lidar():
 def test_candidate_table_exact(oracle, request, which, K):
     """Per-scan K-NN: same K-nearest SET as the reference's brute force (MinK), emitted ascending (d0^2, index)."""
     pb = request.getfixturevalue(which)
-    icp = make_icp(pb, iterations=0, KNN_count=K, max_dist=3.0)
+    icp = make_icp(pb, iterations=0, KNN_count=K, max_dist=3.0, debug_corr=True)
     assert icp.stein_align() == sv.ALIGN_SUCCESS
     idx, rel = icp.get_candidates(want_rel=True)
     q0 = oracle.transform_q0(pb.source, pb.R0, pb.t0)
@@ -64,7 +64,7 @@ def test_candidate_table_tiny_map(oracle):
     """N_t < K: the reference zero-pads (knn.cu:343) -> padded slots point at map point 0."""
     pb = synth.make_uniform_problem(5, 60, 60, seed=16, box=8.0)
     pb.target = pb.target[:10].copy()
-    icp = make_icp(pb, iterations=0, KNN_count=16)
+    icp = make_icp(pb, iterations=0, KNN_count=16, debug_corr=True)
     icp.stein_align()
     idx = icp.get_candidates()
     q0 = oracle.transform_q0(pb.source, pb.R0, pb.t0)
@@ -274,19 +274,15 @@ def test_errors(small):
 
 
 @pytest.mark.parametrize("P,full,es", [(64, True, False), (64, False, False), (1, True, False), (200, True, True), (9, False, True)])
-def test_fused_tail_same_bits(lidar, monkeypatch, P, full, es):
+def test_fused_tail_same_bits(lidar, P, full, es):
     """The cooperative one-kernel Stein phase (tail_fused.cu, default) against the nine separate kernels
-    (SVNICP_NO_FUSED_TAIL=1): same arithmetic and summation orders -> identical particles, history and stop iteration."""
+    (SVNICP_FLAG_SPLIT_TAIL): same arithmetic and summation orders -> identical particles, history and stop iteration."""
     rng = np.random.default_rng(P)
     init = synth.init_particles(P, rng)
     res = {}
     for mode in ("separate", "fused"):
-        if mode == "separate":
-            monkeypatch.setenv("SVNICP_NO_FUSED_TAIL", "1")
-        else:
-            monkeypatch.delenv("SVNICP_NO_FUSED_TAIL", raising=False)
         icp = sv.SVNICP(sv.SteinICPParam(iterations=14, KNN_count=50, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
-                                         convergence_threshold=3e-3), init)
+                                         convergence_threshold=3e-3, flags=sv.FLAG_SPLIT_TAIL if mode == "separate" else 0), init)
         icp.add_cloud(lidar.source[::3], lidar.target, init)
         icp.set_initial_mean(lidar.R0, lidar.t0)
         icp.stein_align()
@@ -298,53 +294,67 @@ def test_fused_tail_same_bits(lidar, monkeypatch, P, full, es):
     assert res["fused"][4] < res["separate"][4]
 
 
-@pytest.mark.parametrize("odd", [False, True])
-def test_pair_mode_same_bits(oracle, lidar, monkeypatch, odd):
-    """SVNICP_GN_PAIR=1 (packed fp32x2 kernels, two source points per thread step) must choose exactly the same
-    correspondences and produce the same poses as the default scalar kernels; odd N_s exercises the half-empty last pair."""
-    src = lidar.source[:-1] if odd else lidar.source
-    res = {}
-    for mode in ("scalar", "pair"):
-        if mode == "pair":
-            monkeypatch.setenv("SVNICP_GN_PAIR", "1")
-        else:
-            monkeypatch.delenv("SVNICP_GN_PAIR", raising=False)
-        icp = sv.SVNICP(sv.SteinICPParam(iterations=1, KNN_count=100, max_dist=3.0, lr=1.0, debug_corr=True), lidar.init_pose)
-        icp.add_cloud(src, lidar.target, lidar.init_pose)
-        icp.set_initial_mean(lidar.R0, lidar.t0)
-        icp.stein_align()
-        xf, idx, mask = icp.get_correspondences()
-        H, b, _ = icp.get_gn_system()
-        res[mode] = (xf, idx, mask, H, b, icp.get_particles())
-    for k in range(3):
-        np.testing.assert_array_equal(res["pair"][k], res["scalar"][k])
-    np.testing.assert_allclose(res["pair"][3], res["scalar"][3], rtol=2e-6)
-    np.testing.assert_allclose(res["pair"][5], res["scalar"][5], rtol=0, atol=1e-7)
-    cidx, rel = icp.get_candidates(want_rel=True)
-    oidx, omask = oracle.corr_f32(res["pair"][0], icp.get_source_f32(), rel, cidx, 3.0)
-    np.testing.assert_array_equal(res["pair"][1], oidx)
-
-
-def test_list_reuse_same_bits(lidar, monkeypatch):
+def test_list_reuse_same_bits(lidar):
     """k_filter_reuse (pruning the previous iteration's lists once they are short) must choose exactly the same
-    correspondences as pruning the full K-slot table every iteration (SVNICP_FILTER_FULL=1): bit-identical poses."""
+    correspondences as pruning the full K-slot table every iteration (SVNICP_FLAG_FILTER_FULL): bit-identical poses."""
     res = {}
     for mode in ("reuse", "full"):
-        if mode == "full":
-            monkeypatch.setenv("SVNICP_FILTER_FULL", "1")
-        else:
-            monkeypatch.delenv("SVNICP_FILTER_FULL", raising=False)
-        icp = sv.SVNICP(sv.SteinICPParam(iterations=25, KNN_count=100, max_dist=3.0, lr=1.0), lidar.init_pose)
+        flags = sv.FLAG_REUSE_STATS | (sv.FLAG_FILTER_FULL if mode == "full" else 0)
+        icp = sv.SVNICP(sv.SteinICPParam(iterations=25, KNN_count=100, max_dist=3.0, lr=1.0, flags=flags), lidar.init_pose)
         icp.add_cloud(lidar.source, lidar.target, lidar.init_pose)
         icp.set_initial_mean(lidar.R0, lidar.t0)
         icp.stein_align()
-        monkeypatch.setenv("SVNICP_DEBUG_REUSE", "1")
         hits = icp.get_prune_stats()
-        monkeypatch.delenv("SVNICP_DEBUG_REUSE")
         res[mode] = (icp.get_particles(), icp.get_particle_history(), hits)
     np.testing.assert_array_equal(res["reuse"][0], res["full"][0])
     np.testing.assert_array_equal(res["reuse"][1], res["full"][1])
     assert res["reuse"][2][-1] > 0.99 and res["full"][2].max() == 0.0  # the reuse path really ran in the late iterations
+
+
+@pytest.mark.parametrize("cls,es", [("svn", False), ("svn", True), ("svgd", False)])
+def test_align_twice_without_add_cloud(oracle, small, cls, es):
+    """stein_align may be called again without add_cloud (the reference allows it: R_/t_ persist, history rows 0..I-1 are
+    rewritten, SVGDICP rebuilds its optimizer, SVGDICP.cpp:73).  The second run must restart the iteration state -- no
+    history row beyond I, no stale stop flag -- and equal one continuous oracle run from the poses of the first."""
+    I = 5
+    if cls == "svn":
+        prm = sv.SteinICPParam(iterations=I, KNN_count=20, max_dist=3.0, lr=1.0, check_early_stop=es, convergence_threshold=1e-2 if es else 1e-5)
+        icp = sv.SVNICP(prm, small.init_pose)
+    else:
+        prm = sv.SteinICPParam(iterations=I, KNN_count=20, max_dist=3.0, lr=0.01, optimizer="Adam")
+        icp = sv.SVGDICP(prm, small.init_pose)
+    icp.add_cloud(small.source, small.target, small.init_pose)
+    icp.set_initial_mean(small.R0, small.t0)
+    assert icp.stein_align() == sv.ALIGN_SUCCESS
+    it1, p1, h1 = icp.iterations_done(), icp.get_particles().reshape(6, -1).copy(), icp.get_particle_history().copy()
+    assert icp.stein_align() == sv.ALIGN_SUCCESS
+    it2, p2, h2 = icp.iterations_done(), icp.get_particles().reshape(6, -1), icp.get_particle_history()
+    assert h2.shape == h1.shape and 0 < it2 <= I
+    if cls == "svn":
+        # the second run starts where the first ended: its first history row is the state after the first run
+        np.testing.assert_allclose(h2[0].reshape(6, -1), p1, atol=1e-6, rtol=0)
+        if es:
+            assert np.abs(p2 - p1).max() > 0  # a stop flag left over from the first run must not turn the second into a no-op
+        else:
+            assert it1 == it2 == I
+            # 2 x I iterations == one oracle run of 2 I iterations
+            o = oracle.align(orc.make_params(iterations=2 * I, knn_count=20, max_dist=3.0, lr=1.0, svn_full_grad=True),
+                             small.source, small.target, small.init_pose, small.R0, small.t0)
+            np.testing.assert_allclose(p2, o["particles"], atol=5 * POSE_TOL, rtol=0)
+    else:
+        assert np.isfinite(p2).all() and np.abs(p2 - p1).max() > 0
+
+
+def test_set_k_keeps_the_clouds(oracle, small):
+    """set_k (SVGDICP.h:98) only changes K_source_: the next stein_align uses the new K on the stored clouds."""
+    icp = make_icp(small, iterations=0, KNN_count=20, max_dist=3.0, debug_corr=True)
+    icp.set_k(7)
+    assert icp.stein_align() == sv.ALIGN_SUCCESS  # no second add_cloud
+    idx = icp.get_candidates()
+    assert idx.shape[1] == 7
+    q0 = oracle.transform_q0(small.source, small.R0, small.t0)
+    oidx, _ = oracle.cand_sorted(q0, small.target, 7)
+    np.testing.assert_array_equal(idx, oidx)
 
 
 def test_against_the_reference_running_on_this_gpu(tmp_path):
