@@ -80,7 +80,6 @@ typedef struct {
 /* svnicp_params.flags (all default off; none changes a result beyond the documented summation-order effects) */
 #define SVNICP_FLAG_NO_PARTICLE_SORT 1  /* keep the caller's particle order internally (no pose-space ordering)      */
 #define SVNICP_FLAG_FILTER_FULL 2       /* prune from the full K-slot candidate table every iteration (no list reuse) */
-#define SVNICP_FLAG_SPLIT_TAIL 4        /* Stein phase as separate kernels (decide, 5 median passes, Stein, update)   */
 #define SVNICP_FLAG_NCCL_GATHER 8       /* sharded: ncclAllGather per iteration instead of the peer-memory exchange    */
 #define SVNICP_FLAG_REUSE_STATS 16      /* svnicp_get_prune_stats reports the fraction of rows served by list reuse    */
 
@@ -107,8 +106,10 @@ const char *svnicp_last_error(svnicp_handle h); /* h may be NULL: last creation 
 int svnicp_set_stream(svnicp_handle h, void *cuda_stream);
 
 /* Particle sharding across the GPUs of one box (no reference counterpart):
- * every rank owns particles [rank*P/n, (rank+1)*P/n) and one ncclAllGather per iteration carries
- * the packed per-particle record.  unique_id: 128 bytes from svnicp_nccl_unique_id on rank 0,
+ * every rank owns particles [rank*P/n, (rank+1)*P/n).  SVN-ICP class: the ranks map each other's record buffers through
+ * CUDA IPC and the owner of a particle stores its record straight into every peer over NVLink (no collective call per
+ * iteration; needs one process per GPU); if that cannot be set up, or with SVNICP_FLAG_NCCL_GATHER, and for the SVGD-ICP
+ * class, one ncclAllGather per iteration carries the packed per-particle records instead.  unique_id: 128 bytes from svnicp_nccl_unique_id on rank 0,
  * distributed by the caller (MPI / torch.distributed / files).  libnccl.so.2 is dlopen'ed. */
 int svnicp_nccl_unique_id(void *id128);
 int svnicp_init_sharding(svnicp_handle h, const void *unique_id128, int rank, int n_ranks);
@@ -168,8 +169,6 @@ int svnicp_set_profiling(svnicp_handle h, int on);
 int svnicp_get_phase_times(svnicp_handle h, double out8[8]);
 /* {n_s, n_t, K, brute-force fallback queries of the candidate builder, TB, n_slices, n_pgroups, iterations enqueued} */
 int svnicp_get_scan_info(svnicp_handle h, int64_t out8[8]);
-/* globaltimer stamps (ns) of the phase boundaries inside the last fused Stein-phase kernel (CTA 0): tuning aid */
-int svnicp_get_tail_stamps(svnicp_handle h, double out10[10]);
 /* number of kernel launches issued by the last svnicp_align */
 int svnicp_get_launch_count(svnicp_handle h, int64_t *out);
 

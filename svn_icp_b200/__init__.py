@@ -41,7 +41,6 @@ class _CParams(C.Structure):
 # svnicp_params.flags (include/svnicp_b200.h): A/B switches read once at construction
 FLAG_NO_PARTICLE_SORT = 1
 FLAG_FILTER_FULL = 2
-FLAG_SPLIT_TAIL = 4
 FLAG_NCCL_GATHER = 8
 FLAG_REUSE_STATS = 16
 
@@ -85,7 +84,7 @@ EXPORTS = [
     "svnicp_initialize_particles", "svnicp_initialize_particles_gaussian", "svnicp_iterations_done", "svnicp_get_candidates",
     "svnicp_get_source_f32", "svnicp_get_correspondences", "svnicp_get_gn_system", "svnicp_get_stein", "svnicp_get_prune_stats",
     "svnicp_get_timing", "svnicp_get_slice", "svnicp_get_launch_count", "svnicp_set_profiling", "svnicp_get_phase_times",
-    "svnicp_get_scan_info", "svnicp_get_tail_stamps",
+    "svnicp_get_scan_info",
     "svnicp_map_create", "svnicp_map_destroy", "svnicp_map_last_error", "svnicp_map_clear", "svnicp_map_add_cloud", "svnicp_map_get",
     "svnicp_map_download", "svnicp_map_size",
     "svnicp_pre_create", "svnicp_pre_destroy", "svnicp_pre_last_error", "svnicp_pre_crop", "svnicp_pre_downsample_uniform",
@@ -141,7 +140,6 @@ def _ARGTYPES(V, I, L, D):
         "svnicp_get_gn_system": [V, V, V, V], "svnicp_get_stein": [V, V, V], "svnicp_get_prune_stats": [V, V, V],
         "svnicp_get_timing": [V, V], "svnicp_get_slice": [V, V, V], "svnicp_get_launch_count": [V, V],
         "svnicp_set_profiling": [V, I], "svnicp_get_phase_times": [V, V], "svnicp_get_scan_info": [V, V],
-        "svnicp_get_tail_stamps": [V, V],
         "svnicp_map_create": [V, D, D, I, L, I], "svnicp_map_clear": [V], "svnicp_map_add_cloud": [V, V, L, I, I, V, V],
         "svnicp_map_get": [V, V, D, V, V], "svnicp_map_download": [V, V, L], "svnicp_map_size": [V, V, V],
         "svnicp_pre_create": [V, L, I], "svnicp_pre_crop": [V, V, L, I, D, D, V, V, V],
@@ -388,11 +386,6 @@ class SVNICP:
         self._check(self._lib.svnicp_get_scan_info(self._h, _p(out)), "get_scan_info")
         names = ["n_s", "n_t", "K", "knn_fallback_queries", "TB", "n_slices", "n_pgroups", "iterations_enqueued"]
         return dict(zip(names, out.tolist()))
-
-    def get_tail_stamps(self):
-        out = np.zeros(10)
-        self._check(self._lib.svnicp_get_tail_stamps(self._h, _p(out)), "get_tail_stamps")
-        return out
 
     def launch_count(self) -> int:
         v = C.c_int64(0)

@@ -81,6 +81,19 @@ struct svnicp_handle_t {
   int rank = 0, n_ranks = 1;
   ncclComm_t comm = nullptr;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // SVN-ICP class: k_head runs on a high-priority side stream and overlaps the correspondence + Gauss-Newton pass
+  cudaStream_t head_stream = nullptr;
+  cudaEvent_t ev_x = nullptr, ev_head = nullptr;
+  // record block: [2][rec_stride] doubles (double buffered by iteration parity) + the peer-exchange flag block; one cudaMalloc,
+  // exported to the other ranks through CUDA IPC when sharded
+  unsigned char *shared_blk = nullptr;
+  size_t rec_records = 0, rec_stride = 0;
+  double *rec = nullptr;
+  unsigned *flags_dev = nullptr;
+  void *peer_base[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool peer_mode = false;  // sharded: peer-memory exchange (true) or one ncclAllGather per iteration (false)
+  unsigned seq = 0;        // sequence number of the last published exchange (monotonic over scans, identical on every rank)
+  PeerTable pt;
   std::string err;
   int K = 100;
   double max_dist = 1.0;
@@ -90,7 +103,7 @@ struct svnicp_handle_t {
   bool have_cloud = false, aligned = false, shape_dirty = false;
   ScanConst sc;
   // device buffers
-  DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, rec, xs, delta, Hbar_inv, stats, particles, init_pose, prep_scratch_d;
+  DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, xs, delta, Hbar_inv, stats, particles, init_pose, prep_scratch_d;
   DevBuf<int> prep_scratch_i;
   // SVGD-ICP class state (class_type = SVGDICP): parameters, pose_particles_ carried between scans, optimizer moments
   DevBuf<double> pose6, prev, opt_state;
@@ -274,15 +287,28 @@ static int alloc_particle_state(svnicp_handle h) {
   CU(h->R.ensure(9 * P, true));
   CU(h->t.ensure(3 * P, true));
   CU(h->dnorm.ensure(P, true));
-  CU(h->rec.ensure(P * REC, true));
-  CU(h->xs.ensure(39 * P));  // SoA copy of the gathered record (RT_ROWS x P)
+  if (!h->shared_blk) {
+    // sized once for any later sharding (P_pad <= P + n_ranks - 1): never reallocated, so IPC mappings stay valid
+    h->rec_records = (((size_t)h->P + MAX_RANKS + REC_TILE_PAD - 1) / REC_TILE_PAD) * REC_TILE_PAD + REC_TILE_PAD;
+    h->rec_stride = h->rec_records * REC;
+    const size_t bytes = 2 * h->rec_stride * sizeof(double) + 256;
+    CU(cudaMalloc((void **)&h->shared_blk, bytes));
+    CU(cudaMemset(h->shared_blk, 0, bytes));
+    h->rec = reinterpret_cast<double *>(h->shared_blk);
+    h->flags_dev = reinterpret_cast<unsigned *>(h->shared_blk + 2 * h->rec_stride * sizeof(double));
+  }
+  memset(&h->pt, 0, sizeof(h->pt));
+  h->pt.n_ranks = 1; h->pt.rank = 0;
+  h->pt.rec[0] = h->rec; h->pt.flag[0] = h->flags_dev;
+  h->pt.timeout_ns = 4000000000ull;
+  CU(h->xs.ensure(39 * P));  // SoA copy of x (SVGD-ICP class: of the gathered record, RT_ROWS x P)
   CU(h->delta.ensure(6 * P, true));
   CU(h->Hbar_inv.ensure(36));
   CU(h->stats.ensure(48));
   CU(h->particles.ensure(6 * P));
   CU(h->xf.ensure(12 * P));
   CU(h->hist.ensure((size_t)MED_PASSES * MED_BINS));
-  CU(h->prep_scratch_d.ensure((size_t)h->sm_count * 12 + 64, true));
+  CU(h->prep_scratch_d.ensure((size_t)(h->P_l_max > h->sm_count ? h->P_l_max : h->sm_count) * 12 + 64, true));  // per-CTA centre partials of k_tail
   CU(h->prep_scratch_i.ensure(PRUNE_BINS + 8, true));
   CU(h->ctrl.ensure(1, true));
   CU(h->misc.ensure(8, true));
@@ -344,6 +370,13 @@ int svnicp_create(svnicp_handle *out, const svnicp_params *params, int particle_
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    {
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&h->head_stream, cudaStreamNonBlocking, hi));
+    }
+    CU(cudaEventCreateWithFlags(&h->ev_x, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming));
     for (int i = 0; i < 4; i++) CU(cudaEventCreate(&h->ev[i]));
     init_iter_kernels();
     CU(cudaGetLastError());
@@ -377,8 +410,15 @@ void svnicp_destroy(svnicp_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->head_stream) cudaStreamSynchronize(h->head_stream);
+  for (int r = 0; r < MAX_RANKS; r++)
+    if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  DevBuf<double> *d[] = {&h->src64, &h->tgt64, &h->q0, &h->sxyz, &h->R, &h->t, &h->dnorm, &h->part, &h->rec, &h->xs, &h->delta,
+  if (h->shared_blk) cudaFree(h->shared_blk);
+  if (h->ev_x) cudaEventDestroy(h->ev_x);
+  if (h->ev_head) cudaEventDestroy(h->ev_head);
+  if (h->head_stream) cudaStreamDestroy(h->head_stream);
+  DevBuf<double> *d[] = {&h->src64, &h->tgt64, &h->q0, &h->sxyz, &h->R, &h->t, &h->dnorm, &h->part, &h->xs, &h->delta,
                          &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose, &h->prep_scratch_d, &h->pose6, &h->prev, &h->opt_state};
   h->prep_scratch_i.release();
   for (auto *b : d) b->release();
@@ -442,6 +482,56 @@ int svnicp_init_sharding(svnicp_handle h, const void *unique_id128, int rank, in
   int r = alloc_particle_state(h);
   if (r) return r;
   h->have_cloud = false;
+  h->peer_mode = false;
+  if (n_ranks > 1 && n_ranks <= MAX_RANKS && h->class_type == SVNICP_CLASS_SVNICP && !(h->prm.flags & SVNICP_FLAG_NCCL_GATHER)) {
+    // Peer-memory exchange: map every rank's record block here through CUDA IPC (handles travel over the NCCL communicator
+    // that exists anyway).  Any failure on any rank -> all ranks fall back to one ncclAllGather per iteration.
+    struct Slot { cudaIpcMemHandle_t hdl; int ok; int pad[15]; };
+    static_assert(sizeof(Slot) == 128, "Slot size");
+    Slot *dev = nullptr;
+    std::vector<Slot> host((size_t)n_ranks);
+    CU(cudaMalloc((void **)&dev, sizeof(Slot) * n_ranks));
+    Slot mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = cudaIpcGetMemHandle(&mine.hdl, h->shared_blk) == cudaSuccess ? 1 : 0;
+    if (!mine.ok) cudaGetLastError();
+    CU(cudaMemcpyAsync(dev + rank, &mine, sizeof(Slot), cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllGather(dev + rank, dev, sizeof(Slot), ncclChar, h->comm, h->stream));
+    CU(cudaMemcpyAsync(host.data(), dev, sizeof(Slot) * n_ranks, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int ok = 1;
+    for (int q = 0; q < n_ranks; q++) ok &= host[q].ok;
+    if (ok)
+      for (int q = 0; q < n_ranks && ok; q++) {
+        if (q == rank) continue;
+        if (cudaIpcOpenMemHandle(&h->peer_base[q], host[q].hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          h->peer_base[q] = nullptr;
+          ok = 0;
+        }
+      }
+    // second round: everybody must have mapped everybody
+    mine.ok = ok;
+    CU(cudaMemcpyAsync(dev + rank, &mine, sizeof(Slot), cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllGather(dev + rank, dev, sizeof(Slot), ncclChar, h->comm, h->stream));
+    CU(cudaMemcpyAsync(host.data(), dev, sizeof(Slot) * n_ranks, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(dev);
+    for (int q = 0; q < n_ranks; q++) ok &= host[q].ok;
+    if (ok) {
+      h->peer_mode = true;
+      h->pt.n_ranks = n_ranks;
+      h->pt.rank = rank;
+      for (int q = 0; q < n_ranks; q++) {
+        unsigned char *base = q == rank ? h->shared_blk : (unsigned char *)h->peer_base[q];
+        h->pt.rec[q] = reinterpret_cast<double *>(base);
+        h->pt.flag[q] = reinterpret_cast<unsigned *>(base + 2 * h->rec_stride * sizeof(double));
+      }
+    } else {
+      for (int q = 0; q < MAX_RANKS; q++)
+        if (h->peer_base[q]) { cudaIpcCloseMemHandle(h->peer_base[q]); h->peer_base[q] = nullptr; }
+    }
+  }
   return SVNICP_OK;
 }
 
@@ -560,10 +650,11 @@ int svnicp_set_threshold(svnicp_handle h, double max_dist) {
   return SVNICP_OK;
 }
 
-static int do_allgather(svnicp_handle h) {
+static int do_allgather(svnicp_handle h, int buf = 0) {
   if (h->n_ranks <= 1) return SVNICP_OK;
   // in place: this rank's block already sits at rec + p_lo*REC
-  NC(g_nccl.AllGather(h->rec.p + (size_t)h->p_lo * REC, h->rec.p, (size_t)h->P_l_max * REC, ncclDouble, h->comm, h->stream));
+  double *base = h->rec + (size_t)buf * h->rec_stride;
+  NC(g_nccl.AllGather(base + (size_t)h->p_lo * REC, base, (size_t)h->P_l_max * REC, ncclDouble, h->comm, h->stream));
   return SVNICP_OK;
 }
 
@@ -574,6 +665,7 @@ int svnicp_align(svnicp_handle h) {
   cudaStream_t st = h->stream;
   const int I = h->prm.iterations;
   h->launches = 0;
+  const bool realign = h->aligned;  // stein_align again without a fresh add_cloud: continue from the current poses
   if (h->shape_dirty) {
     const int rc = prepare_scan(h);
     if (rc) return rc;
@@ -611,8 +703,8 @@ int svnicp_align(svnicp_handle h) {
     // untouched pose_particles_ (every rank holds all of it)
     SteinArgs sa0;
     memset(&sa0, 0, sizeof(sa0));
-    sa0.P = h->P; sa0.rec = h->rec.p; sa0.stats = h->stats.p; sa0.particles = h->particles.p;
-    h->launches += launch_svgd_rec(h->rec.p, h->prev.p, nullptr, 0, h->P, 0, st);
+    sa0.P = h->P; sa0.rec = h->rec; sa0.stats = h->stats.p; sa0.particles = h->particles.p;
+    h->launches += launch_svgd_rec(h->rec, h->prev.p, nullptr, 0, h->P, 0, st);
     h->launches += launch_stats_svgd(sa0, nullptr, st);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h->h_stats, h->stats.p, 48 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -664,7 +756,7 @@ int svnicp_align(svnicp_handle h) {
   ia.sc = h->sc;
   ia.max_dist = (float)h->max_dist;
   ia.sp = h->sp.p; ia.cand = h->cand.p; ia.clist = h->clist.p; ia.ccount = h->ccount.p;
-  ia.R = h->R.p; ia.t = h->t.p; ia.xf = h->xf.p; ia.dnorm = h->dnorm.p; ia.part = h->part.p; ia.rec = h->rec.p; ia.ctrl = h->ctrl.p;
+  ia.R = h->R.p; ia.t = h->t.p; ia.xf = h->xf.p; ia.dnorm = h->dnorm.p; ia.part = h->part.p; ia.rec = h->rec; ia.rec_stride = h->rec_stride; ia.ctrl = h->ctrl.p;
   ia.TB = h->TB; ia.stages = h->stages; ia.n_slices = h->n_slices; ia.n_pgroups = h->n_pgroups; ia.PG = h->PG; ia.RG = h->RG;
   ia.gn_smem = h->gn_smem; ia.sm_count = h->sm_count; ia.svn_full_grad = h->prm.SVN_full_grad;
   ia.first_order = svgd ? 1 : 0;
@@ -676,15 +768,19 @@ int svnicp_align(svnicp_handle h) {
   sa.P = h->P; sa.p_lo = h->p_lo; sa.P_l = h->P_l; sa.I = I;
   sa.svn_full_grad = h->prm.SVN_full_grad; sa.check_early_stop = h->prm.check_early_stop;
   sa.lr = h->prm.lr; sa.threshold = h->prm.convergence_threshold;
-  sa.rec = h->rec.p; sa.xs = h->xs.p; sa.delta = h->delta.p; sa.dnorm = h->dnorm.p; sa.R = h->R.p; sa.t = h->t.p;
+  sa.rec = h->rec; sa.rec_stride = h->rec_stride; sa.xs = h->xs.p; sa.delta = h->delta.p; sa.dnorm = h->dnorm.p; sa.R = h->R.p; sa.t = h->t.p;
   sa.Hbar_inv = h->Hbar_inv.p; sa.hist = h->hist.p; sa.history = h->history.p; sa.ctrl = h->ctrl.p;
   sa.stats = h->stats.p; sa.particles = h->particles.p; sa.sm_count = h->sm_count;
   sa.kept_hist = h->kept_hist.p;
   sa.prep_scratch_d = h->prep_scratch_d.p;
   sa.prep_scratch_i = h->prep_scratch_i.p;
-  // one cooperative kernel per iteration for decide + median + Stein + update + next prep (tail_fused.cu);
-  // SVNICP_FLAG_SPLIT_TAIL keeps the nine separate launches (A/B measurements, same-bits test)
-  const bool fused_tail = !svgd && !(h->prm.flags & SVNICP_FLAG_SPLIT_TAIL);
+  // SVN-ICP class: k_head (decide + median) on the side stream as soon as the poses of the iteration are final, overlapping
+  // k_filter / k_gn; k_finalize and k_tail follow on the main stream.  Sharded without the peer exchange (NCCL fallback):
+  // finalize -> ncclAllGather of the records -> k_head -> k_tail, all on the main stream.
+  const bool overlap = !svgd && (h->n_ranks == 1 || h->peer_mode);
+  PeerTable pt = h->pt;  // n_ranks == 1 view unless the peer exchange is up
+  const unsigned seq0 = h->seq;
+  cudaStream_t hs = h->head_stream;
 
   if (h->profile)
     while (h->prof_events.size() < (size_t)I * 7) {
@@ -692,6 +788,12 @@ int svnicp_align(svnicp_handle h) {
       CU(cudaEventCreate(&pe));
       h->prof_events.push_back(pe);
     }
+  if (!svgd) {
+    // head of the scan: x of every particle into record buffer 0, transforms and pruning ball of the local slice
+    const double *x_src = (realign && h->n_ranks > 1) ? h->rec + (size_t)(h->iters_done & 1) * h->rec_stride : nullptr;
+    h->launches += launch_prep(ia, st, 1, x_src);
+    if (overlap) CU(cudaEventRecord(h->ev_x, st));
+  }
   // ---- iterations (SVNICP.cpp:52-108) ----
   const int LAG = 3;
   int e = 0;
@@ -703,7 +805,14 @@ int svnicp_align(svnicp_handle h) {
     }
 #define PROF(k) do { if (h->profile) CU(cudaEventRecord(h->prof_events[(size_t)e * 7 + (k)], st)); } while (0)
     PROF(0);
-    if (!fused_tail || e == 0) h->launches += launch_prep(ia, st, 0);  // the fused tail prepares the next iteration itself
+    if (svgd) h->launches += launch_prep(ia, st, 0, nullptr);
+    else if (overlap) {
+      CU(cudaStreamWaitEvent(hs, h->ev_x, 0));
+      const int n = launch_head(sa, pt, (h->peer_mode && e > 0) ? seq0 + (unsigned)e : 0u, 0, hs);
+      if (n < 0) return fail(h, SVNICP_ERR_CUDA, "cooperative launch of k_head failed: %s", cudaGetErrorString(cudaGetLastError()));
+      h->launches += n;
+      CU(cudaEventRecord(h->ev_head, hs));
+    }
     PROF(1);
     if (h->filter_reuse) {  // ping-pong: iteration e prunes the lists of iteration e-1 wherever its ball still covers this one's
       const int cur = e & 1;
@@ -724,25 +833,30 @@ int svnicp_align(svnicp_handle h) {
       CU(cudaMemcpyAsync(h->dbg_xf.p, h->xf.p, (size_t)h->P_l * 12 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     PROF(3);
-    h->launches += svgd ? launch_finalize_first(ia, sv, st) : launch_finalize(ia, st);
-    PROF(4);
-    int rc = do_allgather(h);
-    if (rc) return rc;
-    PROF(5);
-    if (fused_tail) {
-      const int n = launch_tail_fused(sa, ia, st);
-      if (n < 0) return fail(h, SVNICP_ERR_CUDA, "cooperative launch of k_tail_fused failed: %s", cudaGetErrorString(cudaGetLastError()));
-      h->launches += n;
-    } else {
+    if (svgd) {
+      h->launches += launch_finalize_first(ia, sv, st);
+      PROF(4);
+      int rc = do_allgather(h);
+      if (rc) return rc;
+      PROF(5);
       h->launches += launch_decide(sa, st, 0);
       h->launches += launch_median(sa, st);
-      if (svgd) {
-        h->launches += launch_stein_first(sa, st);
-        h->launches += launch_update_opt(sa, sv, e + 1, st);
-      } else {
-        h->launches += launch_stein(sa, st);
-        h->launches += launch_update(sa, st);
+      h->launches += launch_stein_first(sa, st);
+      h->launches += launch_update_opt(sa, sv, e + 1, st);
+    } else {
+      if (overlap) CU(cudaStreamWaitEvent(st, h->ev_head, 0));  // stop flag and bandwidth of this iteration
+      h->launches += launch_finalize(ia, pt, seq0 + (unsigned)e + 1u, st);
+      PROF(4);
+      if (!overlap) {
+        int rc = do_allgather(h, e & 1);  // NCCL fallback: whole records (x of this iteration + b, H, g)
+        if (rc) return rc;
+        const int n = launch_head(sa, pt, 0u, 0, st);
+        if (n < 0) return fail(h, SVNICP_ERR_CUDA, "cooperative launch of k_head failed: %s", cudaGetErrorString(cudaGetLastError()));
+        h->launches += n;
       }
+      PROF(5);
+      h->launches += launch_tail(sa, ia, pt, seq0 + (unsigned)e + 1u, seq0 + (unsigned)e + 1u, st);
+      if (overlap) CU(cudaEventRecord(h->ev_x, st));
     }
     PROF(6);
 #undef PROF
@@ -753,16 +867,26 @@ int svnicp_align(svnicp_handle h) {
     }
   }
   h->enqueued_iters = e;
+  h->seq = seq0 + (unsigned)e + 1u;
   CU(cudaEventRecord(h->ev[2], st));
-  // ---- epilogue: final x, last stop decision / history row, getters (SVNICP.cpp:111, :281-308) ----
-  if (svgd) h->launches += launch_svgd_rec(h->rec.p, h->pose6.p, h->dnorm.p, h->p_lo, h->P_l, h->p_lo, st);
-  else h->launches += launch_prep(ia, st, 1);
-  {
+  // ---- epilogue: last stop decision / history row, getters (SVNICP.cpp:111, :281-308) ----
+  if (svgd) {
+    h->launches += launch_svgd_rec(h->rec, h->pose6.p, h->dnorm.p, h->p_lo, h->P_l, h->p_lo, st);
     int rc = do_allgather(h);
     if (rc) return rc;
+    h->launches += launch_decide(sa, st, 1);
+    h->launches += launch_stats_svgd(sa, h->prev.p, st);
+  } else {
+    // the final x of every particle already sits in the record buffer of parity (updates applied & 1) on every rank
+    if (!overlap && h->n_ranks > 1)
+      for (int b2 = 0; b2 < 2; b2++) {  // NCCL fallback: the device knows which buffer is final (early stop), so gather both
+        int rc = do_allgather(h, b2);
+        if (rc) return rc;
+      }
+    const int n = launch_head(sa, pt, (h->peer_mode && e > 0) ? seq0 + (unsigned)e : 0u, 1, st);
+    if (n < 0) return fail(h, SVNICP_ERR_CUDA, "cooperative launch of k_head failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += n + launch_stats(sa, 1, st);
   }
-  h->launches += launch_decide(sa, st, 1);
-  h->launches += svgd ? launch_stats_svgd(sa, h->prev.p, st) : launch_stats(sa, st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(h->h_stats, h->stats.p, 48 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h->h_particles, h->particles.p, (size_t)6 * h->P * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -771,6 +895,7 @@ int svnicp_align(svnicp_handle h) {
   CU(cudaEventRecord(h->ev[3], st));
   CU(cudaStreamSynchronize(st));
   h->iters_done = h->h_ctrl->iters_done;
+  if (h->h_ctrl->error) return fail(h, SVNICP_ERR_CUDA, "peer exchange timed out: another rank did not publish its records (rank %d of %d)", h->rank, h->n_ranks);
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->ms_setup = ms;
   cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->ms_iter = ms;
@@ -946,10 +1071,15 @@ int svnicp_get_gn_system(svnicp_handle h, double *out_H, double *out_b, double *
   if (!h || !h->aligned) return fail(h, SVNICP_ERR_INVALID, "no scan yet");
   CU(cudaSetDevice(h->device));
   std::vector<double> rec((size_t)h->P * REC);
-  CU(cudaMemcpy(rec.data(), h->rec.p, rec.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  // x at the head of the last executed iteration lives in xs [6][P] (the epilogue rewrites rec's x with the final poses)
+  // SVN-ICP class: the record of the last executed iteration k = iters_done - 1 (x at its head, b, H) is in buffer k & 1
+  const int buf = (h->class_type == SVNICP_CLASS_SVNICP && h->iters_done > 0) ? ((h->iters_done - 1) & 1) : 0;
+  CU(cudaMemcpy(rec.data(), h->rec + (size_t)buf * h->rec_stride, rec.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  // SVGD-ICP class: x at the head of the last executed iteration lives in xs [6][P] (the epilogue rewrites rec's x)
   std::vector<double> xs((size_t)6 * h->P);
-  CU(cudaMemcpy(xs.data(), h->xs.p, xs.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h->class_type != SVNICP_CLASS_SVNICP) CU(cudaMemcpy(xs.data(), h->xs.p, xs.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  else
+    for (int i = 0; i < h->P; i++)
+      for (int c = 0; c < 6; c++) xs[(size_t)c * h->P + i] = rec[(size_t)i * REC + REC_X + c];
   for (int i = 0; i < h->P; i++) {  // i: internal order, p: the caller's particle index
     const double *r = rec.data() + (size_t)i * REC;
     const size_t p = h->permuted ? (size_t)h->perm[i] : (size_t)i;
@@ -1022,13 +1152,6 @@ int svnicp_get_scan_info(svnicp_handle h, int64_t out8[8]) {
   if (!h || !out8) return SVNICP_ERR_INVALID;
   out8[0] = h->n_s; out8[1] = h->n_t; out8[2] = h->K; out8[3] = h->fallback_queries;
   out8[4] = h->TB; out8[5] = h->n_slices; out8[6] = h->n_pgroups; out8[7] = h->enqueued_iters;
-  return SVNICP_OK;
-}
-
-int svnicp_get_tail_stamps(svnicp_handle h, double out10[10]) {
-  if (!h || !out10) return SVNICP_ERR_INVALID;
-  CU(cudaSetDevice(h->device));
-  CU(cudaMemcpy(out10, h->prep_scratch_d.p + (size_t)h->sm_count * 12, 10 * sizeof(double), cudaMemcpyDeviceToHost));
   return SVNICP_OK;
 }
 

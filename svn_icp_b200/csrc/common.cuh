@@ -16,8 +16,10 @@
 
 namespace svn {
 
-// packed per-particle record, REC doubles
-constexpr int REC = 40;
+// packed per-particle record, REC doubles.  41, not 40: tiles of records are staged AoS in shared memory by 1-D bulk TMA and
+// read with lane = particle; an odd stride in doubles makes those reads bank-conflict free (40 would be a 16-way conflict)
+constexpr int REC = 41;
+constexpr int REC_TILE_PAD = 256;  // the record buffers hold a multiple of this many records, zero filled: every tile copy is full size
 constexpr int REC_X = 0;       // [0,6)   x = [t ; Log R] at the head of the iteration
 constexpr int REC_B = 6;       // [6,12)  b = sum J^T rho e
 constexpr int REC_H = 12;      // [12,33) H upper triangle, row-major
@@ -36,7 +38,9 @@ struct Ctrl {
   int stop;         // 1 once the early stop fired (all later kernels return immediately)
   int iter;         // iterations whose pose update has been applied
   int iters_done;   // == iter at the moment of the stop
-  int pad0;
+  int error;        // 1: a wait on a peer's flag timed out (sharded handles); the host reports it after the scan
+  unsigned fin_ticket, tail_ticket;  // CTAs of k_finalize / k_tail that have finished (the last one publishes)
+  unsigned pad1, pad2;
   double bandwidth;  // h of the last Stein step
   // exact-pruning ball of the local particle slice (k_prep): |q_pb - qbar_b| <= alpha*|s'_b| + beta
   float Abar[9];
@@ -49,6 +53,20 @@ struct Ctrl {
   unsigned long long sel_rank[MED_PASSES + 1];
   unsigned med_ticket[MED_PASSES];  // CTAs that finished pass s (the last one selects)
   unsigned long long kept_total;  // sum of ccount over rows (prune statistics)
+};
+
+// ---- peer-memory exchange of the per-particle records between the GPUs of one box (sharded handles) -----------------
+// Every rank owns a block [2][rec_stride] doubles (records, double buffered by iteration parity) + a flag block, mapped
+// into every other rank through CUDA IPC.  The owner of a particle stores its record fields straight into every rank's
+// buffer over NVLink and then publishes a sequence number in that rank's flag block; consumers spin on their LOCAL flags.
+constexpr int MAX_RANKS = 8;
+constexpr int FLAG_H = 0;  // "b, H (g) of iteration seq are in your buffer"   (k_finalize -> k_tail)
+constexpr int FLAG_X = 1;  // "x, |delta| after update seq are in your buffer" (k_tail -> k_head)
+struct PeerTable {
+  int n_ranks, rank;
+  double *rec[MAX_RANKS];     // record block of rank r as mapped HERE (rec[rank] = the local block)
+  unsigned *flag[MAX_RANKS];  // flag block of rank r: [kind * MAX_RANKS + source rank]
+  unsigned long long timeout_ns;
 };
 
 struct ScanConst {  // per-scan constants, passed by value

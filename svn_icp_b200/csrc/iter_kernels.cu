@@ -22,45 +22,17 @@
 // operation by operation in oracle/svn_oracle.c (oracle_corr_f32) for the bit-exact index parity test.
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace svn {
 
 // ---------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk TMA
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-// ---------------------------------------------------------------------------------------------
 // k_prep
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_prep(IterArgs a, int x_only) {
+// all_x (SVN-ICP class, head of a scan): x = [t ; Log R] of EVERY particle goes into record buffer 0 -- each rank can do that
+// alone because add_cloud gives every rank all initial poses; x_src != null (stein_align called again without add_cloud on a
+// sharded handle, where R, t of the other ranks' particles are stale): their x is carried over from the previous result.
+__global__ void __launch_bounds__(1024) k_prep(IterArgs a, int all_x, const double *x_src) {
   if (a.ctrl->stop) return;
   __shared__ double s_red[32][12];
   __shared__ float s_center[12];
@@ -84,7 +56,6 @@ __global__ void __launch_bounds__(1024) k_prep(IterArgs a, int x_only) {
 #pragma unroll
     for (int i = 0; i < 3; i++) { rec[REC_X + i] = t[i]; rec[REC_X + 3 + i] = w[i]; }
     rec[REC_DNORM] = a.dnorm[l];
-    if (x_only) continue;  // scan epilogue: only the final poses are needed
     // A' = R0 (R - I) R0^T, tau = R0 t   (so that q_pb - q0_b = A' (R0 s_b) + tau)
     double D[9], T[9], M[9];
 #pragma unroll
@@ -107,7 +78,23 @@ __global__ void __launch_bounds__(1024) k_prep(IterArgs a, int x_only) {
       acc[9 + r] += (double)f;
     }
   }
-  if (x_only) return;
+  if (all_x)
+    for (int p = tid; p < a.P; p += blockDim.x) {
+      if (p >= a.p_lo && p < a.p_lo + a.P_l) continue;
+      double *rec = a.rec + (size_t)p * REC;
+      if (x_src) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) rec[REC_X + i] = x_src[(size_t)p * REC + REC_X + i];
+      } else {
+        double R[9], w[3];
+#pragma unroll
+        for (int i = 0; i < 9; i++) R[i] = a.R[9 * (size_t)p + i];
+        so3_log(R, w);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { rec[REC_X + i] = a.t[3 * (size_t)p + i]; rec[REC_X + 3 + i] = w[i]; }
+      }
+      rec[REC_DNORM] = 0.0;
+    }
 #pragma unroll
   for (int i = 0; i < 12; i++) acc[i] = warp_sum(acc[i]);
   if (lane == 0)
@@ -619,73 +606,99 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_finalize: partials -> reference H (upper triangle) and b; one warp per particle
+// k_finalize: partials -> reference H (upper triangle) and b; one CTA per particle.  The record fields it produces (b, H, g)
+// go into the record buffer of this iteration's parity on EVERY rank (peer stores over NVLink when sharded); the CTA that
+// finishes last publishes the sequence number in the peers' flag blocks (k_tail waits for it).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_finalize(IterArgs a) {
-  if (a.ctrl->stop) return;
+__global__ void __launch_bounds__(128) k_finalize(IterArgs a, PeerTable pt, unsigned seq_h) {
+  Ctrl *ctl = a.ctrl;
+  if (ctl->stop) return;
+  __shared__ double s_out[REC];
+  __shared__ int s_last;
   const int l = blockIdx.x;  // one CTA (FIN_WARPS warps) per local particle
   double v[NACC];
   gn_sum_partials(a, l, v);
-  if (threadIdx.x != 0) return;
   const int p = a.p_lo + l;
-  const double *R0 = a.sc.R0;
-  double Rp[9], Rt[9];
+  const size_t buf_off = (size_t)(ctl->iter & 1) * a.rec_stride;
+  if (threadIdx.x == 0) {
+    const double *R0 = a.sc.R0;
+    double Rp[9], Rt[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) Rp[i] = a.R[9 * (size_t)p + i];
+    for (int i = 0; i < 9; i++) Rp[i] = a.R[9 * (size_t)p + i];
 #pragma unroll
-  for (int r = 0; r < 3; r++)
+    for (int r = 0; r < 3; r++)
 #pragma unroll
-    for (int c = 0; c < 3; c++) Rt[3 * r + c] = R0[3 * r] * Rp[c] + R0[3 * r + 1] * Rp[3 + c] + R0[3 * r + 2] * Rp[6 + c];
-  const double W = v[0];
-  // world-oriented -> sensor frame: S1 = R0^T S1', S2 = R0^T S2' R0
-  const double S1p[3] = {v[1], v[2], v[3]};
-  const double S2p[9] = {v[4], v[5], v[6], v[5], v[7], v[8], v[6], v[8], v[9]};
-  double S1[3], T[9], S2[9];
+      for (int c = 0; c < 3; c++) Rt[3 * r + c] = R0[3 * r] * Rp[c] + R0[3 * r + 1] * Rp[3 + c] + R0[3 * r + 2] * Rp[6 + c];
+    const double W = v[0];
+    // world-oriented -> sensor frame: S1 = R0^T S1', S2 = R0^T S2' R0
+    const double S1p[3] = {v[1], v[2], v[3]};
+    const double S2p[9] = {v[4], v[5], v[6], v[5], v[7], v[8], v[6], v[8], v[9]};
+    double S1[3], T[9], S2[9];
 #pragma unroll
-  for (int c = 0; c < 3; c++) S1[c] = R0[c] * S1p[0] + R0[3 + c] * S1p[1] + R0[6 + c] * S1p[2];
+    for (int c = 0; c < 3; c++) S1[c] = R0[c] * S1p[0] + R0[3 + c] * S1p[1] + R0[6 + c] * S1p[2];
 #pragma unroll
-  for (int r = 0; r < 3; r++)
+    for (int r = 0; r < 3; r++)
 #pragma unroll
-    for (int c = 0; c < 3; c++) T[3 * r + c] = R0[r] * S2p[c] + R0[3 + r] * S2p[3 + c] + R0[6 + r] * S2p[6 + c];
+      for (int c = 0; c < 3; c++) T[3 * r + c] = R0[r] * S2p[c] + R0[3 + r] * S2p[3 + c] + R0[6 + r] * S2p[6 + c];
 #pragma unroll
-  for (int r = 0; r < 3; r++)
+    for (int r = 0; r < 3; r++)
 #pragma unroll
-    for (int c = 0; c < 3; c++) S2[3 * r + c] = T[3 * r] * R0[c] + T[3 * r + 1] * R0[3 + c] + T[3 * r + 2] * R0[6 + c];
-  double H[36];
+      for (int c = 0; c < 3; c++) S2[3 * r + c] = T[3 * r] * R0[c] + T[3 * r + 1] * R0[3 + c] + T[3 * r + 2] * R0[6 + c];
+    double H[36];
 #pragma unroll
-  for (int i = 0; i < 36; i++) H[i] = 0.0;
-  const double trS2 = S2[0] + S2[4] + S2[8];
-  for (int i = 0; i < 3; i++) {
-    H[7 * i] = W + 1e-6;  // SVNICP.cpp:153 (Q3); translation block = sum(rho') + #masked (Q2)
-    for (int j = 0; j < 3; j++) H[6 * (3 + i) + 3 + j] = ((i == j) ? trS2 : 0.0) - S2[3 * i + j];
-    H[7 * (3 + i)] += 1e-6;
-  }
-  // H_tr = -[S1]x
-  H[0 * 6 + 4] = S1[2];  H[0 * 6 + 5] = -S1[1];
-  H[1 * 6 + 3] = -S1[2]; H[1 * 6 + 5] = S1[0];
-  H[2 * 6 + 3] = S1[1];  H[2 * 6 + 4] = -S1[0];
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) H[6 * (3 + i) + j] = H[6 * j + 3 + i];
-  double b[6];
-  // b_t = R~^T E, b_r = R~^T C
+    for (int i = 0; i < 36; i++) H[i] = 0.0;
+    const double trS2 = S2[0] + S2[4] + S2[8];
+    for (int i = 0; i < 3; i++) {
+      H[7 * i] = W + 1e-6;  // SVNICP.cpp:153 (Q3); translation block = sum(rho') + #masked (Q2)
+      for (int j = 0; j < 3; j++) H[6 * (3 + i) + 3 + j] = ((i == j) ? trS2 : 0.0) - S2[3 * i + j];
+      H[7 * (3 + i)] += 1e-6;
+    }
+    // H_tr = -[S1]x
+    H[0 * 6 + 4] = S1[2];  H[0 * 6 + 5] = -S1[1];
+    H[1 * 6 + 3] = -S1[2]; H[1 * 6 + 5] = S1[0];
+    H[2 * 6 + 3] = S1[1];  H[2 * 6 + 4] = -S1[0];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) H[6 * (3 + i) + j] = H[6 * j + 3 + i];
+    double b[6];
+    // b_t = R~^T E, b_r = R~^T C
 #pragma unroll
-  for (int c = 0; c < 3; c++) {
-    b[c] = Rt[c] * v[10] + Rt[3 + c] * v[11] + Rt[6 + c] * v[12];
-    b[3 + c] = Rt[c] * v[13] + Rt[3 + c] * v[14] + Rt[6 + c] * v[15];
-  }
-  double *rec = a.rec + (size_t)p * REC;
+    for (int c = 0; c < 3; c++) {
+      b[c] = Rt[c] * v[10] + Rt[3 + c] * v[11] + Rt[6 + c] * v[12];
+      b[3 + c] = Rt[c] * v[13] + Rt[3 + c] * v[14] + Rt[6 + c] * v[15];
+    }
 #pragma unroll
-  for (int i = 0; i < 6; i++) rec[REC_B + i] = b[i];
-  for (int r = 0; r < 6; r++)
-    for (int c = r; c < 6; c++) rec[REC_H + tri(r, c)] = H[6 * r + c];
-  if (!a.svn_full_grad) {  // g = H^-1 b, SVNICP.cpp:162 (only consumed by the pre-conditioned SVGD step)
+    for (int i = 0; i < 6; i++) s_out[REC_B + i] = b[i];
+    for (int r = 0; r < 6; r++)
+      for (int c = r; c < 6; c++) s_out[REC_H + tri(r, c)] = H[6 * r + c];
     double g[6];
 #pragma unroll
-    for (int i = 0; i < 6; i++) g[i] = b[i];
-    lu_solve6(H, g, 1);
+    for (int i = 0; i < 6; i++) g[i] = 0.0;
+    if (!a.svn_full_grad) {  // g = H^-1 b, SVNICP.cpp:162 (only consumed by the pre-conditioned SVGD step)
 #pragma unroll
-    for (int i = 0; i < 6; i++) rec[REC_G + i] = g[i];
+      for (int i = 0; i < 6; i++) g[i] = b[i];
+      lu_solve6(H, g, 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) s_out[REC_G + i] = g[i];
   }
+  __syncthreads();
+  // fields [REC_B, REC_DNORM) and [REC_G, REC_G + 6) of the particle's record on every rank; x and |delta| belong to k_tail
+  for (int u = threadIdx.x; u < pt.n_ranks * 33; u += blockDim.x) {
+    const int r = u / 33, f = u % 33;
+    const int field = f < 27 ? REC_B + f : REC_G + (f - 27);
+    pt.rec[r][buf_off + (size_t)p * REC + field] = s_out[field];
+  }
+  if (pt.n_ranks <= 1) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->fin_ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  if ((int)threadIdx.x < pt.n_ranks && (int)threadIdx.x != pt.rank) {
+    __threadfence_system();
+    st_release_sys(pt.flag[threadIdx.x] + FLAG_H * MAX_RANKS + pt.rank, seq_h);
+  }
+  if (threadIdx.x == 0) ctl->fin_ticket = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -700,8 +713,8 @@ void init_iter_kernels() {
 #undef SVN_GN_ATTR
 }
 
-int launch_prep(const IterArgs &a, cudaStream_t st, int x_only) {
-  k_prep<<<1, 1024, 0, st>>>(a, x_only);
+int launch_prep(const IterArgs &a, cudaStream_t st, int all_x, const double *x_src) {
+  k_prep<<<1, 1024, 0, st>>>(a, all_x, x_src);
   return 1;
 }
 
@@ -747,8 +760,8 @@ int launch_gn(const IterArgs &a, cudaStream_t st) {
   return 1;
 }
 
-int launch_finalize(const IterArgs &a, cudaStream_t st) {
-  if (a.P_l > 0) k_finalize<<<a.P_l, FIN_WARPS * 32, 0, st>>>(a);
+int launch_finalize(const IterArgs &a, const PeerTable &pt, unsigned seq_h, cudaStream_t st) {
+  if (a.P_l > 0) k_finalize<<<a.P_l, FIN_WARPS * 32, 0, st>>>(a, pt, seq_h);
   return 1;
 }
 

@@ -54,7 +54,8 @@ struct IterArgs {
   float *xf;           // [P_l][12]
   double *dnorm;       // [P_l]
   double *part;        // [n_slices*RG][P_l][NACC]
-  double *rec;         // [P_pad][REC]
+  double *rec;         // [2][rec_stride]: records [P_rec][REC], double buffered by iteration parity (SVGD-ICP class: buffer 0 only)
+  size_t rec_stride;   // doubles per record buffer
   Ctrl *ctrl;
   // launch shape of the Gauss-Newton kernel
   int TB, stages, n_slices, n_pgroups, PG, RG;
@@ -100,10 +101,10 @@ __device__ __forceinline__ void gn_sum_partials(const IterArgs &a, int l, double
   }
 }
 #endif
-int launch_prep(const IterArgs &a, cudaStream_t st, int x_only);
+int launch_prep(const IterArgs &a, cudaStream_t st, int all_x, const double *x_src);
 int launch_filter(const IterArgs &a, cudaStream_t st);
 int launch_gn(const IterArgs &a, cudaStream_t st);
-int launch_finalize(const IterArgs &a, cudaStream_t st);
+int launch_finalize(const IterArgs &a, const PeerTable &pt, unsigned seq_h, cudaStream_t st);
 void init_iter_kernels();
 // bytes of one shared-memory stage of k_gn: TB pruned rows of K float4 + TB source points + TB counts
 __host__ __device__ inline size_t gn_stage_bytes(int TB, int K) { return (size_t)TB * K * 16 + (size_t)TB * 16 + (size_t)TB * 4; }
@@ -112,8 +113,9 @@ struct SteinArgs {
   int P, p_lo, P_l, I;
   int svn_full_grad, check_early_stop;
   double lr, threshold;
-  double *rec;       // [P_pad][REC]
-  double *xs;        // [6][P] SoA copy of x
+  double *rec;       // [2][rec_stride] (see IterArgs)
+  size_t rec_stride;
+  double *xs;        // [6][P] SoA copy of x (SVGD-ICP class: [39][P] copy of the gathered record)
   double *delta;     // [P_l][6]
   double *dnorm;     // [P_l]
   double *R, *t;
@@ -128,13 +130,16 @@ struct SteinArgs {
   int *prep_scratch_i;            // [PRUNE_BINS + 3] envelope / alpha / beta / NaN flag maxima (bit patterns)
   int sm_count;
 };
-// the whole Stein phase of one iteration as ONE cooperative kernel (tail_fused.cu); returns launches or -1
-int launch_tail_fused(const SteinArgs &a, const IterArgs &ia, cudaStream_t st);
+// SVN-ICP class, Stein phase (tail2.cu): k_head = early-stop decision + history row + exact median bandwidth (cooperative,
+// small grid, off the critical path); k_tail = Stein step + pose update + next iteration's transforms and pruning ball.
+// seq_x / seq_h / seq_x_out: sequence numbers of the peer exchange (0 = nothing to wait for).  Return launches or -1.
+int launch_head(const SteinArgs &a, const PeerTable &pt, unsigned seq_x, int epilogue, cudaStream_t st);
+int launch_tail(const SteinArgs &a, const IterArgs &ia, const PeerTable &pt, unsigned seq_h, unsigned seq_x_out, cudaStream_t st);
+// SVGD-ICP class: separate kernels on the gathered record (stein_kernels.cu, svgd_class.cu)
 int launch_decide(const SteinArgs &a, cudaStream_t st, int epilogue);
 int launch_median(const SteinArgs &a, cudaStream_t st);
-int launch_stein(const SteinArgs &a, cudaStream_t st);
-int launch_update(const SteinArgs &a, cudaStream_t st);
-int launch_stats(const SteinArgs &a, cudaStream_t st);
+// getters from the record buffer; parity_from_ctrl: read the buffer of parity (iters_done & 1) (SVN-ICP class)
+int launch_stats(const SteinArgs &a, int parity_from_ctrl, cudaStream_t st);
 // restart of the device-side iteration state at the head of every stein_align (poses are kept)
 int launch_align_reset(Ctrl *ctrl, double *opt_state, size_t n_opt, cudaStream_t st);
 int launch_init_particles(double *R, double *t, const double *init_pose_dev, int P, double *dnorm, int p_lo, int P_l, Ctrl *ctrl,

@@ -1,17 +1,13 @@
-// stein_kernels.cu -- the Stein Variational Newton step (north_star kernel (c)) and the scan epilogue.
+// stein_kernels.cu -- particle initialisation, the separate decide / radix-median kernels (SVGD-ICP class) and the getters.
+// (The SVN-ICP class runs its Stein phase in tail2.cu: k_head + k_tail.)
 //
-// Replaces, per iteration of SVNICP::stein_align (reference svn-icp/src/core/SVNICP.cpp):
-//   rbf_hessian_kernel   :254-266  pairwise squared distances, LOWER median over all P^2 entries
-//                                  (torch::median), K = exp(-D/h)   -> exact 5-pass radix select, the
-//                                  [P,P] matrices are never materialised
-//   svn_full_grad        :229-252  kernel-weighted Hessians, one 6x6 solve per particle in registers
-//   svgd_grad            :218-227  pre-conditioned SVGD step (shipped default SVNFullGrad=false)
-//   pose_update          :268-279  right-multiplicative update with the left Jacobian
-//   early stop           :95-101   decided on the device; later kernels become no-ops
-//   history row          :103-107  float32 [6][P]
-//   getters              :281-308  weighted mean / variance / covariance
-// All fp64.  Summation order over j is fixed (lane-strided, xor tree) so that an N-GPU run reproduces
-// the 1-GPU Stein step bit for bit.
+// Kept here (both classes / SVGD-ICP class):
+//   k_particles_init     SVGDICP::add_cloud :46-61 with SVNICP's Exp (SVNICP.cpp:166-194)
+//   k_align_reset        head of every stein_align
+//   k_decide             early stop :95-101, history row :103-107, SoA copy of the gathered record   (SVGD-ICP class)
+//   k_median_pass x 5    rbf kernel bandwidth: LOWER median over all P^2 entries (torch::median), exact radix select
+//   k_stats              getters :281-308  weighted mean / variance / covariance
+// All fp64.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -41,7 +37,10 @@ __global__ void k_particles_init(double *R, double *t, const double *init_pose, 
 // reference does) but with fresh iteration counters, stop flag and -- SVGD-ICP class -- optimizer moments (SVGDICP.cpp:73).
 __global__ void k_align_reset(Ctrl *ctrl, double *opt_state, size_t n_opt) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { ctrl->stop = 0; ctrl->iter = 0; ctrl->iters_done = 0; ctrl->kept_total = 0ull; }
+  if (i == 0) {
+    ctrl->stop = 0; ctrl->iter = 0; ctrl->iters_done = 0; ctrl->kept_total = 0ull;
+    ctrl->error = 0; ctrl->fin_ticket = 0u; ctrl->tail_ticket = 0u;
+  }
   for (size_t k = i; k < n_opt; k += (size_t)gridDim.x * blockDim.x) opt_state[k] = 0.0;
 }
 
@@ -206,230 +205,12 @@ __global__ void __launch_bounds__(MED_THREADS) k_median_pass(SteinArgs a, int s)
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_stein_full: SVNICP::svn_full_grad (SVNICP.cpp:229-252).  A CTA owns ST_NI particles i; each is served by ST_JQ warps
-// that split every 128-wide j tile of the 33-double record (staged in shared memory) into quarters; lane = j.
-// Fixed summation order (lane-strided per quarter, xor tree, quarters 0..3), identical on every rank.
-// ---------------------------------------------------------------------------------------------
-constexpr int ST_WARPS = 8;
-constexpr int ST_TJ = 32;    // j-tile of the pre-conditioned SVGD kernel
-constexpr int ST_TJF = 128;  // j-tile of the full SVN kernel
-constexpr int ST_JQ = 2;     // warps per particle
-constexpr int ST_NI = ST_WARPS / ST_JQ;
-
-__global__ void __launch_bounds__(ST_WARPS * 32) k_stein_full(SteinArgs a) {
-  Ctrl *c = a.ctrl;
-  if (c->stop) return;
-  __shared__ double s_rec[33][ST_TJF + 1];
-  __shared__ double s_part[ST_WARPS][28];
-  const double h = c->bandwidth;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ii = warp / ST_JQ, jq = warp % ST_JQ;
-  const int l = blockIdx.x * ST_NI + ii;
-  const bool active = l < a.P_l;
-  const int i = a.p_lo + (active ? l : 0);
-  double xi[6];
-#pragma unroll
-  for (int d = 0; d < 6; d++) xi[d] = a.rec[(size_t)i * REC + REC_X + d];
-  double Hm[21], v[6];
-#pragma unroll
-  for (int q = 0; q < 21; q++) Hm[q] = 0.0;
-#pragma unroll
-  for (int q = 0; q < 6; q++) v[q] = 0.0;
-  const double two_over_h = 2.0 / h;
-  for (int j0 = 0; j0 < a.P; j0 += ST_TJF) {
-    __syncthreads();
-    {
-      // coalesced rows of the SoA record copy; all loads are issued before the first store (one L2 round trip per tile)
-      constexpr int NLD = (33 * ST_TJF + ST_WARPS * 32 - 1) / (ST_WARPS * 32);
-      double tmp[NLD];
-#pragma unroll
-      for (int u = 0; u < NLD; u++) {
-        const int e = tid + u * ST_WARPS * 32;
-        const int q = e / ST_TJF, jj = e % ST_TJF;
-        tmp[u] = (e < 33 * ST_TJF && j0 + jj < a.P) ? __ldg(a.xs + (size_t)q * a.P + j0 + jj) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < NLD; u++) {
-        const int e = tid + u * ST_WARPS * 32;
-        if (e < 33 * ST_TJF) s_rec[e / ST_TJF][e % ST_TJF] = tmp[u];
-      }
-    }
-    __syncthreads();
-    for (int u = 0; u < ST_TJF / 32 / ST_JQ; u++) {  // this warp's share of the tile, ascending j (fixed order)
-    const int jj = (jq * (ST_TJF / 32 / ST_JQ) + u) * 32 + lane;
-    if (active && j0 + jj < a.P) {
-      double dl[6], D = 0.0;
-#pragma unroll
-      for (int d = 0; d < 6; d++) { dl[d] = xi[d] - s_rec[REC_X + d][jj]; D += dl[d] * dl[d]; }
-      const double kij = exp(-D / h);          // :264
-      const double k2 = kij * kij;             // :238
-      double g[6];
-#pragma unroll
-      for (int d = 0; d < 6; d++) g[d] = two_over_h * (dl[d] * kij);  // :233
-      int q = 0;
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int cc = r; cc < 6; cc++, q++) Hm[q] += k2 * s_rec[REC_H + q][jj] + g[r] * g[cc];  // :236-242
-#pragma unroll
-      for (int d = 0; d < 6; d++) v[d] += g[d] - kij * s_rec[REC_B + d][jj];  // :244 with b' = -b
-    }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 21; q++) Hm[q] = warp_sum(Hm[q]);
-#pragma unroll
-  for (int q = 0; q < 6; q++) v[q] = warp_sum(v[q]);
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < 21; q++) s_part[warp][q] = Hm[q];
-#pragma unroll
-    for (int q = 0; q < 6; q++) s_part[warp][21 + q] = v[q];
-  }
-  __syncthreads();
-  if (active && jq == 0 && lane == 0) {
-    double A[36], x[6];
-    for (int r = 0; r < 6; r++)
-      for (int cc = r; cc < 6; cc++) {
-        double sum = 0.0;
-        for (int w = 0; w < ST_JQ; w++) sum += s_part[ii * ST_JQ + w][tri(r, cc)];
-        A[6 * r + cc] = sum / (double)a.P;
-        A[6 * cc + r] = A[6 * r + cc];
-      }
-    for (int d = 0; d < 6; d++) {
-      double sum = 0.0;
-      for (int w = 0; w < ST_JQ; w++) sum += s_part[ii * ST_JQ + w][21 + d];
-      x[d] = sum / (double)a.P;
-    }
-    lu_solve6(A, x, 1);  // :250 (the reference forms the explicit inverse; tolerance-level difference)
-    for (int d = 0; d < 6; d++) a.delta[(size_t)l * 6 + d] = a.lr * x[d];
-  }
-}
-
-// mean Hessian and its inverse for the pre-conditioned SVGD step (SVNICP.cpp:85, :225). One CTA.
-__global__ void __launch_bounds__(1024) k_mean_hessian(SteinArgs a) {
-  Ctrl *c = a.ctrl;
-  if (c->stop) return;
-  __shared__ double s_sum[32][21];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double acc[21];
-#pragma unroll
-  for (int q = 0; q < 21; q++) acc[q] = 0.0;
-  for (int p = tid; p < a.P; p += blockDim.x)
-#pragma unroll
-    for (int q = 0; q < 21; q++) acc[q] += a.rec[(size_t)p * REC + REC_H + q];
-#pragma unroll
-  for (int q = 0; q < 21; q++) acc[q] = warp_sum(acc[q]);
-  if (lane == 0)
-#pragma unroll
-    for (int q = 0; q < 21; q++) s_sum[warp][q] = acc[q];
-  __syncthreads();
-  if (tid == 0) {
-    double A[36], Inv[36];
-    for (int r = 0; r < 6; r++)
-      for (int cc = r; cc < 6; cc++) {
-        double s = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += s_sum[w][tri(r, cc)];
-        A[6 * r + cc] = s / (double)a.P;
-        A[6 * cc + r] = A[6 * r + cc];
-      }
-    for (int q = 0; q < 36; q++) Inv[q] = (q % 7 == 0) ? 1.0 : 0.0;
-    lu_solve6(A, Inv, 6);
-    for (int q = 0; q < 36; q++) a.Hbar_inv[q] = Inv[q];
-  }
-}
-
-// k_stein_svgd: SVNICP::svgd_grad (SVNICP.cpp:218-227), no lr (Q5)
-__global__ void __launch_bounds__(ST_WARPS * 32) k_stein_svgd(SteinArgs a) {
-  Ctrl *c = a.ctrl;
-  if (c->stop) return;
-  __shared__ double s_rec[12][ST_TJ + 1];
-  const double h = c->bandwidth;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int l = blockIdx.x * ST_WARPS + warp;
-  const bool active = l < a.P_l;
-  const int i = a.p_lo + (active ? l : 0);
-  double xi[6];
-#pragma unroll
-  for (int d = 0; d < 6; d++) xi[d] = a.rec[(size_t)i * REC + REC_X + d];
-  double gs[6], kn[6], ks = 0.0;
-#pragma unroll
-  for (int d = 0; d < 6; d++) { gs[d] = 0.0; kn[d] = 0.0; }
-  for (int j0 = 0; j0 < a.P; j0 += ST_TJ) {
-    __syncthreads();
-    for (int e = tid; e < 12 * ST_TJ; e += blockDim.x) {
-      const int q = e / ST_TJ, jj = e % ST_TJ;
-      const int row = (q < 6) ? q : (33 + q - 6);  // x rows 0..5, g rows 33..38 of the SoA record copy
-      s_rec[q][jj] = (j0 + jj < a.P) ? a.xs[(size_t)row * a.P + j0 + jj] : 0.0;
-    }
-    __syncthreads();
-    if (active && j0 + lane < a.P) {
-      double dl[6], D = 0.0;
-#pragma unroll
-      for (int d = 0; d < 6; d++) { dl[d] = xi[d] - s_rec[d][lane]; D += dl[d] * dl[d]; }
-      const double kij = exp(-D / h);
-      ks += kij;                                                       // :226
-#pragma unroll
-      for (int d = 0; d < 6; d++) { gs[d] += dl[d] * kij; kn[d] -= kij * s_rec[6 + d][lane]; }  // :221-224 (newton passed negated, :86)
-    }
-  }
-  ks = warp_sum(ks);
-#pragma unroll
-  for (int d = 0; d < 6; d++) { gs[d] = warp_sum(gs[d]); kn[d] = warp_sum(kn[d]); }
-  if (active && lane == 0) {
-    const double f = 2.0 / h;
-    for (int r = 0; r < 6; r++) {
-      double s = 0.0;
-      for (int cc = 0; cc < 6; cc++) s += a.Hbar_inv[6 * r + cc] * (f * gs[cc]);
-      a.delta[(size_t)l * 6 + r] = (kn[r] + s) / ks;
-    }
-  }
-}
-
-// P == 1: stein_grad = -H^-1 b (SVNICP.cpp:88-89)
-__global__ void k_stein_single(SteinArgs a) {
-  Ctrl *c = a.ctrl;
-  if (c->stop) return;
-  if (threadIdx.x != 0 || blockIdx.x != 0 || a.P_l < 1) return;
-  double A[36], x[6];
-  const double *rec = a.rec + (size_t)a.p_lo * REC;
-  for (int r = 0; r < 6; r++)
-    for (int cc = r; cc < 6; cc++) { A[6 * r + cc] = rec[REC_H + tri(r, cc)]; A[6 * cc + r] = A[6 * r + cc]; }
-  for (int d = 0; d < 6; d++) x[d] = rec[REC_B + d];
-  lu_solve6(A, x, 1);
-  for (int d = 0; d < 6; d++) a.delta[d] = -x[d];
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_update: SVNICP::pose_update (SVNICP.cpp:268-279) for the local slice
-// ---------------------------------------------------------------------------------------------
-__global__ void k_update(SteinArgs a) {
-  Ctrl *c = a.ctrl;
-  if (c->stop) return;
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l < a.P_l) {
-    const int p = a.p_lo + l;
-    double d[6];
-    for (int i = 0; i < 6; i++) d[i] = a.delta[(size_t)l * 6 + i];
-    double dR[9], Jl[9], R[9], Rn[9], dt[3];
-    so3_exp(d + 3, dR, Jl);  // :269-271 (J_l side effect :188-192)
-    for (int r = 0; r < 3; r++) dt[r] = Jl[3 * r] * d[0] + Jl[3 * r + 1] * d[1] + Jl[3 * r + 2] * d[2];  // :275
-    for (int i = 0; i < 9; i++) R[i] = a.R[9 * (size_t)p + i];
-    for (int r = 0; r < 3; r++)
-      for (int cc = 0; cc < 3; cc++) Rn[3 * r + cc] = R[3 * r] * dR[cc] + R[3 * r + 1] * dR[3 + cc] + R[3 * r + 2] * dR[6 + cc];  // :277
-    for (int i = 0; i < 9; i++) a.R[9 * (size_t)p + i] = Rn[i];
-    for (int r = 0; r < 3; r++)
-      a.t[3 * (size_t)p + r] = (Rn[3 * r] * dt[0] + Rn[3 * r + 1] * dt[1] + Rn[3 * r + 2] * dt[2]) + a.t[3 * (size_t)p + r];  // :278 (Q6)
-    a.dnorm[l] = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);  // :96 norm(2,1)
-  }
-  if (l == 0) c->iter = c->iter + 1;
-}
-
-// ---------------------------------------------------------------------------------------------
 // k_stats: getters (SVNICP.cpp:281-308) from the gathered record.  One CTA.
 // weights = float32(1)/P promoted to double (SVNICP.cpp:46, :281-284).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_stats(SteinArgs a) {
+__global__ void __launch_bounds__(1024) k_stats(SteinArgs a, int parity_from_ctrl) {
+  // SVN-ICP class: the final poses sit in the record buffer of parity (number of updates applied & 1)
+  if (parity_from_ctrl) a.rec += (size_t)(a.ctrl->iters_done & 1) * a.rec_stride;
   __shared__ double s_red[32][36];
   __shared__ double s_mean[6];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -511,28 +292,8 @@ int launch_median(const SteinArgs &a, cudaStream_t st) {
   return MED_PASSES;
 }
 
-int launch_stein(const SteinArgs &a, cudaStream_t st) {
-  if (a.P < 2) {
-    k_stein_single<<<1, 32, 0, st>>>(a);
-    return 1;
-  }
-  const int grid = cdiv(a.P_l, ST_WARPS);
-  if (a.svn_full_grad) {
-    k_stein_full<<<cdiv(a.P_l, ST_NI), ST_WARPS * 32, 0, st>>>(a);
-    return 1;
-  }
-  k_mean_hessian<<<1, 1024, 0, st>>>(a);
-  k_stein_svgd<<<grid, ST_WARPS * 32, 0, st>>>(a);
-  return 2;
-}
-
-int launch_update(const SteinArgs &a, cudaStream_t st) {
-  k_update<<<cdiv(a.P_l, 128), 128, 0, st>>>(a);
-  return 1;
-}
-
-int launch_stats(const SteinArgs &a, cudaStream_t st) {
-  k_stats<<<1, 1024, 0, st>>>(a);
+int launch_stats(const SteinArgs &a, int parity_from_ctrl, cudaStream_t st) {
+  k_stats<<<1, 1024, 0, st>>>(a, parity_from_ctrl);
   return 1;
 }
 

@@ -1,7 +1,8 @@
 """Worker for tests/test_gpu_multi.py: launched with torch.distributed.run, one rank per GPU.
 
-Runs one particle-sharded scan (one ncclAllGather per iteration) and compares it, on rank 0, with the same scan on a
-single GPU.  Exit code 0 = parity."""
+Runs particle-sharded scans (SVN-ICP class: peer-memory record exchange over NVLink, and the ncclAllGather fallback;
+SVGD-ICP class: ncclAllGather) and compares them, on rank 0, with the same scan on a single GPU.  Exit code 0 = parity.
+Slices of >= 64 particles exercise the pose-space particle ordering inside each rank's slice (getters must map back)."""
 import os
 import sys
 
@@ -9,6 +10,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+
+TOL_SVN = 1e-7   # identical algorithm; only the grouping of the fp32 Gauss-Newton partial sums and of the fp64 Stein sums depends on the slice size
+TOL_SVGD = 2e-5  # Adam divides by the running RMS of the gradient, which amplifies that ~1e-7 relative difference (measured 3e-6)
 
 
 def main():
@@ -21,26 +25,37 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    cases = ((96, True, False, "svn"), (37, False, False, "svn"), (64, True, True, "svn"), (48, True, False, "svgd"), (41, True, True, "svgd"))
-    for P, full, es, cls in cases:
+    #        P    full   es     class   flags                 twice
+    cases = ((96, True, False, "svn", 0, False), (37, False, False, "svn", 0, False), (64, True, True, "svn", 0, False),
+             (256, True, False, "svn", 0, False), (300, False, True, "svn", 0, False), (256, True, False, "svn", sv.FLAG_NO_PARTICLE_SORT, False),
+             (200, True, False, "svn", sv.FLAG_NCCL_GATHER, False), (130, True, True, "svn", sv.FLAG_NCCL_GATHER, False),
+             (160, True, False, "svn", 0, True),
+             (48, True, False, "svgd", 0, False), (41, True, True, "svgd", 0, False))
+    for P, full, es, cls, flags, twice in cases:
         pb = synth.make_problem(P, sensor="32", scan_index=6, n_map_scans=6, seed=0xC0FFEE)
         if cls == "svn":
             prm = sv.SteinICPParam(iterations=10, KNN_count=64, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
-                                   convergence_threshold=1e-2)
+                                   convergence_threshold=1e-2, flags=flags)
             make = lambda: sv.SVNICP(prm, pb.init_pose, device=local)
-        else:  # the SVGD-ICP class shards the same way (first-order record, same all-gather)
+        else:  # the SVGD-ICP class shards the same way (first-order record, one all-gather per iteration)
             prm = sv.SteinICPParam(iterations=10, KNN_count=64, max_dist=3.0, lr=0.03, optimizer="Adam", check_early_stop=es,
                                    convergence_threshold=5e-2)
             make = lambda: sv.SVGDICP(prm, pb.init_pose, device=local)
+
+        def scan(h):
+            h.add_cloud(pb.source, pb.target, pb.init_pose)
+            h.set_initial_mean(pb.R0, pb.t0)
+            assert h.stein_align() == sv.ALIGN_SUCCESS
+            if twice:  # stein_align again without add_cloud: the other ranks' x must carry over
+                assert h.stein_align() == sv.ALIGN_SUCCESS
+
         icp = make()
         uid = [sv.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         icp.init_sharding(uid[0], rank, world)
         lo, hi = icp.slice()
         assert hi - lo >= 1 and (hi - lo) <= -(-P // world)
-        icp.add_cloud(pb.source, pb.target, pb.init_pose)
-        icp.set_initial_mean(pb.R0, pb.t0)
-        assert icp.stein_align() == sv.ALIGN_SUCCESS
+        scan(icp)
         got = icp.get_particles()
         mean, cov, its, hist = icp.get_transformation(), icp.get_cov_matrix(), icp.iterations_done(), icp.get_particle_history()
         # every rank must hold the identical full result
@@ -50,18 +65,15 @@ def main():
         same = bool(torch.equal(t, ref))
         if rank == 0:
             single = make()
-            single.add_cloud(pb.source, pb.target, pb.init_pose)
-            single.set_initial_mean(pb.R0, pb.t0)
-            single.stein_align()
+            scan(single)
             err = np.abs(single.get_particles() - got).max()
             herr = np.abs(single.get_particle_history() - hist).max()
-            print(f"{cls} P={P} full={full} es={es} ranks={world}: |sharded - single| particles {err:.3e} history {herr:.3e} "
-                  f"iters {its} vs {single.iterations_done()}", flush=True)
-            # identical algorithm; only the grouping of the fp32 Gauss-Newton partial sums differs with the slice size
-            # (SVGD-ICP class: Adam divides by the running RMS of the gradient, which amplifies that ~1e-7 relative difference
-            # to ~3e-6 in the poses after 10 steps -- measured; bounded by the per-scan tolerance of the class)
-            tol = 1e-7 if cls == "svn" else 2e-5
-            ok &= err < tol and herr < tol + 1e-6 and its == single.iterations_done()
+            tol = TOL_SVN if cls == "svn" else TOL_SVGD
+            good = bool(err < tol and herr < tol + 1e-6 and its == single.iterations_done())
+            print(f"{cls} P={P} full={full} es={es} flags={flags} twice={twice} ranks={world}: |sharded - single| particles {err:.3e} "
+                  f"history {herr:.3e} iters {its} vs {single.iterations_done()} same_on_all_ranks={same} -> {'ok' if good and same else 'FAIL'}",
+                  flush=True)
+            ok &= good
         flag = torch.tensor([1 if (ok and same) else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok = bool(flag.item())

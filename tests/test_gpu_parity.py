@@ -273,25 +273,31 @@ def test_errors(small):
         icp.add_cloud(np.zeros((0, 3)), small.target, np.zeros((6, 4)))
 
 
-@pytest.mark.parametrize("P,full,es", [(64, True, False), (64, False, False), (1, True, False), (200, True, True), (9, False, True)])
-def test_fused_tail_same_bits(lidar, P, full, es):
-    """The cooperative one-kernel Stein phase (tail_fused.cu, default) against the nine separate kernels
-    (SVNICP_FLAG_SPLIT_TAIL): same arithmetic and summation orders -> identical particles, history and stop iteration."""
+@pytest.mark.parametrize("P,full,es", [(64, True, False), (64, False, False), (1, True, False), (200, True, True), (9, False, True),
+                                       (300, True, False), (1200, False, False)])
+def test_stein_phase_layouts_vs_oracle(oracle, lidar, P, full, es):
+    """k_head + k_tail (tail2.cu) over the CTA layouts the particle count selects (8 warps per particle for small P ... one
+    warp per particle for large P, both Stein modes, P == 1, early stop): the scan is deterministic (bit-identical when
+    repeated) and follows the fp64 oracle iteration by iteration."""
     rng = np.random.default_rng(P)
     init = synth.init_particles(P, rng)
-    res = {}
-    for mode in ("separate", "fused"):
-        icp = sv.SVNICP(sv.SteinICPParam(iterations=14, KNN_count=50, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
-                                         convergence_threshold=3e-3, flags=sv.FLAG_SPLIT_TAIL if mode == "separate" else 0), init)
-        icp.add_cloud(lidar.source[::3], lidar.target, init)
+    src = lidar.source[::6]
+    I = 6
+    prm = dict(iterations=I, KNN_count=50, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es, convergence_threshold=3e-3)
+    runs = []
+    for _ in range(2):
+        icp = sv.SVNICP(sv.SteinICPParam(**prm), init)
+        icp.add_cloud(src, lidar.target, init)
         icp.set_initial_mean(lidar.R0, lidar.t0)
-        icp.stein_align()
-        res[mode] = (icp.get_particles(), icp.get_particle_history(), icp.iterations_done(), icp.get_cov_matrix(), icp.launch_count())
-    np.testing.assert_array_equal(res["fused"][0], res["separate"][0])
-    np.testing.assert_array_equal(res["fused"][1], res["separate"][1])
-    assert res["fused"][2] == res["separate"][2]
-    np.testing.assert_array_equal(res["fused"][3], res["separate"][3])
-    assert res["fused"][4] < res["separate"][4]
+        assert icp.stein_align() == sv.ALIGN_SUCCESS
+        runs.append((icp.get_particles(), icp.get_particle_history(), icp.iterations_done(), icp.get_cov_matrix()))
+    for k in range(4):
+        np.testing.assert_array_equal(runs[0][k], runs[1][k])
+    o = oracle.align(orc.make_params(iterations=I, knn_count=50, max_dist=3.0, lr=1.0, svn_full_grad=full, check_early_stop=es,
+                                     convergence_threshold=3e-3), src, lidar.target, init, lidar.R0, lidar.t0)
+    assert runs[0][2] == o["iters_done"]
+    np.testing.assert_allclose(runs[0][0].reshape(6, -1), o["particles"], atol=2 * POSE_TOL, rtol=0)
+    np.testing.assert_allclose(runs[0][1].reshape(I, 6, -1), o["history"], atol=2 * POSE_TOL, rtol=0)
 
 
 def test_list_reuse_same_bits(lidar):
@@ -331,8 +337,9 @@ def test_align_twice_without_add_cloud(oracle, small, cls, es):
     it2, p2, h2 = icp.iterations_done(), icp.get_particles().reshape(6, -1), icp.get_particle_history()
     assert h2.shape == h1.shape and 0 < it2 <= I
     if cls == "svn":
-        # the second run starts where the first ended: its first history row is the state after the first run
-        np.testing.assert_allclose(h2[0].reshape(6, -1), p1, atol=1e-6, rtol=0)
+        # history row e = poses after update e (SVNICP.cpp:103-107): the last row written equals the final particles
+        if not es:
+            np.testing.assert_allclose(h1[-1].reshape(6, -1), p1, atol=1e-6, rtol=0)
         if es:
             assert np.abs(p2 - p1).max() > 0  # a stop flag left over from the first run must not turn the second into a no-op
         else:
