@@ -169,6 +169,9 @@ int svnicp_set_profiling(svnicp_handle h, int on);
 int svnicp_get_phase_times(svnicp_handle h, double out8[8]);
 /* {n_s, n_t, K, brute-force fallback queries of the candidate builder, TB, n_slices, n_pgroups, iterations enqueued} */
 int svnicp_get_scan_info(svnicp_handle h, int64_t out8[8]);
+/* globaltimer stamps (ns) inside the last k_tail launch of the last scan (profiling on): CTA 0 {start, after the peer wait,
+ * after the Stein sums, after the pose update}, last CTA {start of the ball reduction, end}; tuning aid */
+int svnicp_get_tail_stamps(svnicp_handle h, double out8[8]);
 /* number of kernel launches issued by the last svnicp_align */
 int svnicp_get_launch_count(svnicp_handle h, int64_t *out);
 
@@ -219,6 +222,18 @@ int svnicp_pre_crop(svnicp_pre p, const float *xyz, int64_t n, int on_device, do
  * index, first point on ties).  Output order is arbitrary (PCL iterates an unordered_map). */
 int svnicp_pre_downsample_uniform(svnicp_pre p, const float *xyz, int64_t n, int on_device, double leaf, const float **dev_out,
                                   int64_t *n_out);
+/* deskew_pointcloud (OdometryPipeline.cpp:357-447): every point is moved by Pose3::Expmap((s - 0.5) * delta) with
+ * delta = Pose3::Logmap(start^-1 * finish) (the two newest entries of the node's pose buffer, :419-424) and s its time
+ * stamp normalised to [0,1] over the scan (:411-420).  stamps: [n] doubles in any unit (the `t` / `timestamp` / `time` field
+ * of the PointCloud2 message widened to double, :400-410), host or device; kitti != 0 reproduces the KITTI branch instead
+ * (:385-399: 0.205 deg tilt about p x z, stamp from the azimuth; stamps may be NULL).  *moved = 0 when all stamps are equal:
+ * the cloud is returned unchanged (:415).  Poses: rotation row-major 3x3 + translation.  GTSAM's closed forms (4.2) are restated. */
+int svnicp_pre_deskew(svnicp_pre p, const float *xyz, int64_t n, int on_device, const double *stamps, int stamps_on_device, int kitti,
+                      const double R_start[9], const double t_start[3], const double R_finish[9], const double t_finish[3],
+                      const float **dev_out, int32_t *moved);
+/* The hand-off after the getters in ICP mode (updater_, OdometryPipeline.cpp:37-45; tensor2gtsamPose3, ICPUtils.cpp:84-98):
+ * pose = initial_guess * Pose3(Rot3::Expmap(mean[3:6]), mean[0:3]) with mean6 = svnicp_get_transformation().  Host arithmetic. */
+int svnicp_pose_compose(const double R0[9], const double t0[3], const double mean6[6], double R_out[9], double t_out[3]);
 /* float device cloud -> double device cloud (owned by the handle) for svnicp_add_cloud(source_on_device = 1) */
 int svnicp_pre_to_f64(svnicp_pre p, const float *dev_xyz, int64_t n, const double **dev_out);
 int svnicp_pre_download(svnicp_pre p, const float *dev_xyz, int64_t n, float *out);

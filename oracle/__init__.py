@@ -335,6 +335,26 @@ class PreprocessOracle:
         n = self.lib.oracle_downsample_uniform(_ptr(a), C.c_int64(len(a)), C.c_double(radius), _ptr(out))
         return out[:n].copy()
 
+    # ---- de-skewing (OdometryPipeline.cpp:357-447; GTSAM 4.2 closed forms restated, pinned against scipy expm/logm) ----
+    def pose3_expmap(self, xi):
+        R, t = np.zeros((3, 3)), np.zeros(3)
+        self.lib.oracle_pose3_expmap(_ptr(_f64(xi)), _ptr(R), _ptr(t))
+        return R, t
+
+    def pose3_logmap(self, R, t):
+        xi = np.zeros(6)
+        self.lib.oracle_pose3_logmap(_ptr(_f64(R)), _ptr(_f64(t)), _ptr(xi))
+        return xi
+
+    def deskew(self, cloud, stamps, start_pose, finish_pose, kitti=False):
+        a = np.ascontiguousarray(cloud, dtype=np.float32)
+        st = _f64(stamps) if stamps is not None else None
+        out = np.zeros_like(a)
+        (Rs, ts), (Rf, tf) = start_pose, finish_pose
+        moved = self.lib.oracle_deskew(_ptr(a), _ptr(st), C.c_int64(len(a)), C.c_int(int(kitti)), _ptr(_f64(Rs)), _ptr(_f64(ts)),
+                                       _ptr(_f64(Rf)), _ptr(_f64(tf)), _ptr(out))
+        return out, bool(moved)
+
 
 class ReferenceMap:
     """The reference's own svnicp::VoxelHashMap (oracle/_ref/libvmap_ref.so: VoxelHashMap.cpp compiled unmodified over

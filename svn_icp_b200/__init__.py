@@ -84,11 +84,11 @@ EXPORTS = [
     "svnicp_initialize_particles", "svnicp_initialize_particles_gaussian", "svnicp_iterations_done", "svnicp_get_candidates",
     "svnicp_get_source_f32", "svnicp_get_correspondences", "svnicp_get_gn_system", "svnicp_get_stein", "svnicp_get_prune_stats",
     "svnicp_get_timing", "svnicp_get_slice", "svnicp_get_launch_count", "svnicp_set_profiling", "svnicp_get_phase_times",
-    "svnicp_get_scan_info",
+    "svnicp_get_scan_info", "svnicp_get_tail_stamps",
     "svnicp_map_create", "svnicp_map_destroy", "svnicp_map_last_error", "svnicp_map_clear", "svnicp_map_add_cloud", "svnicp_map_get",
     "svnicp_map_download", "svnicp_map_size",
     "svnicp_pre_create", "svnicp_pre_destroy", "svnicp_pre_last_error", "svnicp_pre_crop", "svnicp_pre_downsample_uniform",
-    "svnicp_pre_to_f64", "svnicp_pre_download",
+    "svnicp_pre_to_f64", "svnicp_pre_download", "svnicp_pre_deskew", "svnicp_pose_compose",
 ]
 
 
@@ -139,11 +139,12 @@ def _ARGTYPES(V, I, L, D):
         "svnicp_get_candidates": [V, V, V], "svnicp_get_source_f32": [V, V], "svnicp_get_correspondences": [V, V, V, V],
         "svnicp_get_gn_system": [V, V, V, V], "svnicp_get_stein": [V, V, V], "svnicp_get_prune_stats": [V, V, V],
         "svnicp_get_timing": [V, V], "svnicp_get_slice": [V, V, V], "svnicp_get_launch_count": [V, V],
-        "svnicp_set_profiling": [V, I], "svnicp_get_phase_times": [V, V], "svnicp_get_scan_info": [V, V],
+        "svnicp_get_tail_stamps": [V, V], "svnicp_set_profiling": [V, I], "svnicp_get_phase_times": [V, V], "svnicp_get_scan_info": [V, V],
         "svnicp_map_create": [V, D, D, I, L, I], "svnicp_map_clear": [V], "svnicp_map_add_cloud": [V, V, L, I, I, V, V],
         "svnicp_map_get": [V, V, D, V, V], "svnicp_map_download": [V, V, L], "svnicp_map_size": [V, V, V],
         "svnicp_pre_create": [V, L, I], "svnicp_pre_crop": [V, V, L, I, D, D, V, V, V],
         "svnicp_pre_downsample_uniform": [V, V, L, I, D, V, V], "svnicp_pre_to_f64": [V, V, L, V], "svnicp_pre_download": [V, V, L, V],
+        "svnicp_pre_deskew": [V, V, L, I, V, I, I, V, V, V, V, V, V], "svnicp_pose_compose": [V, V, V, V, V],
     }
 
 
@@ -387,6 +388,11 @@ class SVNICP:
         names = ["n_s", "n_t", "K", "knn_fallback_queries", "TB", "n_slices", "n_pgroups", "iterations_enqueued"]
         return dict(zip(names, out.tolist()))
 
+    def get_tail_stamps(self):
+        out = np.zeros(8)
+        self._check(self._lib.svnicp_get_tail_stamps(self._h, _p(out)), "get_tail_stamps")
+        return out
+
     def launch_count(self) -> int:
         v = C.c_int64(0)
         self._check(self._lib.svnicp_get_launch_count(self._h, C.byref(v)), "get_launch_count")
@@ -408,6 +414,15 @@ class SVGDICP(SVNICP):
 
     def __init__(self, param: SteinICPParam, init_pose, device: int = -1):
         super().__init__(param, init_pose, None, device)
+
+
+def pose_compose(R0, t0, mean6):
+    """ICP-mode updater (OdometryPipeline.cpp:37-45, ICPUtils.cpp:84-98): initial_guess * Pose3(Expmap(mean[3:6]), mean[0:3])."""
+    R, t = np.zeros((3, 3)), np.zeros(3)
+    rc = load_library().svnicp_pose_compose(_p(_f64(R0).reshape(9)), _p(_f64(t0).reshape(3)), _p(_f64(mean6).reshape(6)), _p(R), _p(t))
+    if rc:
+        raise SvnIcpError("pose_compose: invalid argument")
+    return R, t
 
 
 class VoxelHashMap:
@@ -538,6 +553,18 @@ class ScanPreprocessor:
         self._check(self._lib.svnicp_pre_downsample_uniform(self._p, src, C.c_int64(n), C.c_int(int(on_device)), C.c_double(voxel_size),
                                                             C.byref(ptr), C.byref(n_out)), "downsample_uniform")
         return ptr.value, n_out.value
+
+    def deskew_pointcloud(self, cloud, stamps, start_pose, finish_pose, n: int = 0, on_device: bool = False, kitti: bool = False):
+        """OdometryPipeline::deskew_pointcloud (:357-447).  stamps: [n] per-point time stamps (host array; None with kitti=True);
+        start_pose / finish_pose: (R [3,3], t [3]) = the two newest poses of the node's pose buffer.  Returns (device ptr, n, moved)."""
+        src, n, keep = self._src(cloud, n, on_device)
+        st = np.ascontiguousarray(stamps, dtype=np.float64) if stamps is not None else None
+        ptr, moved = C.c_void_p(), C.c_int32(0)
+        (Rs, ts), (Rf, tf) = start_pose, finish_pose
+        self._check(self._lib.svnicp_pre_deskew(self._p, src, C.c_int64(n), C.c_int(int(on_device)), _p(st), C.c_int(0), C.c_int(int(kitti)),
+                                                _p(_f64(Rs).reshape(9)), _p(_f64(ts).reshape(3)), _p(_f64(Rf).reshape(9)), _p(_f64(tf).reshape(3)),
+                                                C.byref(ptr), C.byref(moved)), "deskew_pointcloud")
+        return ptr.value, n, bool(moved.value)
 
     def to_f64(self, ptr: int, n: int) -> int:
         out = C.c_void_p()

@@ -105,6 +105,7 @@ struct svnicp_handle_t {
   // device buffers
   DevBuf<double> src64, tgt64, q0, sxyz, R, t, dnorm, part, xs, delta, Hbar_inv, stats, particles, init_pose, prep_scratch_d;
   DevBuf<int> prep_scratch_i;
+  DevBuf<double> stamps;  // k_tail phase stamps of the last iteration (profiling on)
   // SVGD-ICP class state (class_type = SVGDICP): parameters, pose_particles_ carried between scans, optimizer moments
   DevBuf<double> pose6, prev, opt_state;
   int optimizer = -1;
@@ -310,6 +311,7 @@ static int alloc_particle_state(svnicp_handle h) {
   CU(h->hist.ensure((size_t)MED_PASSES * MED_BINS));
   CU(h->prep_scratch_d.ensure((size_t)(h->P_l_max > h->sm_count ? h->P_l_max : h->sm_count) * 12 + 64, true));  // per-CTA centre partials of k_tail
   CU(h->prep_scratch_i.ensure(PRUNE_BINS + 8, true));
+  CU(h->stamps.ensure(8, true));
   CU(h->ctrl.ensure(1, true));
   CU(h->misc.ensure(8, true));
   const size_t I = (size_t)(h->prm.iterations > 0 ? h->prm.iterations : 1);
@@ -421,6 +423,7 @@ void svnicp_destroy(svnicp_handle h) {
   DevBuf<double> *d[] = {&h->src64, &h->tgt64, &h->q0, &h->sxyz, &h->R, &h->t, &h->dnorm, &h->part, &h->xs, &h->delta,
                          &h->Hbar_inv, &h->stats, &h->particles, &h->init_pose, &h->prep_scratch_d, &h->pose6, &h->prev, &h->opt_state};
   h->prep_scratch_i.release();
+  h->stamps.release();
   for (auto *b : d) b->release();
   h->sp.release(); h->cand.release(); h->clist.release();
   h->clist2.release(); h->ccount2.release();
@@ -774,6 +777,7 @@ int svnicp_align(svnicp_handle h) {
   sa.kept_hist = h->kept_hist.p;
   sa.prep_scratch_d = h->prep_scratch_d.p;
   sa.prep_scratch_i = h->prep_scratch_i.p;
+  sa.stamps = h->profile ? h->stamps.p : nullptr;
   // SVN-ICP class: k_head (decide + median) on the side stream as soon as the poses of the iteration are final, overlapping
   // k_filter / k_gn; k_finalize and k_tail follow on the main stream.  Sharded without the peer exchange (NCCL fallback):
   // finalize -> ncclAllGather of the records -> k_head -> k_tail, all on the main stream.
@@ -1152,6 +1156,13 @@ int svnicp_get_scan_info(svnicp_handle h, int64_t out8[8]) {
   if (!h || !out8) return SVNICP_ERR_INVALID;
   out8[0] = h->n_s; out8[1] = h->n_t; out8[2] = h->K; out8[3] = h->fallback_queries;
   out8[4] = h->TB; out8[5] = h->n_slices; out8[6] = h->n_pgroups; out8[7] = h->enqueued_iters;
+  return SVNICP_OK;
+}
+
+int svnicp_get_tail_stamps(svnicp_handle h, double out8[8]) {
+  if (!h || !out8) return SVNICP_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpy(out8, h->stamps.p, 8 * sizeof(double), cudaMemcpyDeviceToHost));
   return SVNICP_OK;
 }
 

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace svn {
 
 // packed per-particle record, REC doubles.  41, not 40: tiles of records are staged AoS in shared memory by 1-D bulk TMA and
@@ -116,6 +118,46 @@ __device__ inline void lu_solve6(double *A, double *B, int nrhs) {
     }
 }
 
+// The same solve (one right-hand side) with every index a compile-time constant: A and b stay in registers (nvcc leaves
+// `#pragma unroll` loops of this depth rolled and puts A on the stack, hence the template recursion).  The pivot of column k
+// is brought up by compare-and-swap of whole rows (i = k+1 .. 5 against row k): the same pivot VALUES as a classic arg-max
+// search, and each remaining row sees identical arithmetic, so the solution has the same bits (exact ties aside).
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+__device__ __forceinline__ void lu_solve6_reg(double (&A)[36], double (&b)[6]) {
+  static_for<0, 6>([&](auto K) {
+    constexpr int k = decltype(K)::value;
+    static_for<k + 1, 6>([&](auto I_) {
+      constexpr int i = decltype(I_)::value;
+      const bool sw = fabs(A[i * 6 + k]) > fabs(A[k * 6 + k]);
+      static_for<k, 6>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        const double u = A[k * 6 + j], v = A[i * 6 + j];
+        A[k * 6 + j] = sw ? v : u;
+        A[i * 6 + j] = sw ? u : v;
+      });
+      const double u = b[k], v = b[i];
+      b[k] = sw ? v : u;
+      b[i] = sw ? u : v;
+    });
+    const double d = A[k * 6 + k];
+    static_for<k + 1, 6>([&](auto I_) {
+      constexpr int i = decltype(I_)::value;
+      const double l = A[i * 6 + k] / d;
+      static_for<k + 1, 6>([&](auto J) { constexpr int j = decltype(J)::value; A[i * 6 + j] -= l * A[k * 6 + j]; });
+      b[i] -= l * b[k];
+    });
+  });
+  static_for<0, 6>([&](auto KK) {
+    constexpr int k = 5 - decltype(KK)::value;
+    double s = b[k];
+    static_for<k + 1, 6>([&](auto I_) { constexpr int i = decltype(I_)::value; s -= A[k * 6 + i] * b[i]; });
+    b[k] = s / A[k * 6 + k];
+  });
+}
+
 // upper-triangle index of (r,c), r <= c, row-major packing of a symmetric 6x6
 __host__ __device__ __forceinline__ int tri(int r, int c) { return r * 6 - (r * (r - 1)) / 2 + (c - r); }
 
@@ -129,7 +171,9 @@ __device__ inline void so3_exp(const double r[3], double R[9], double *Jl) {
   const double c = cos(a), s = sin(a);
   const double ah[9] = {0, -n[2], n[1], n[2], 0, -n[0], -n[1], n[0], 0};
   const double sa = s / a, ca = (1.0 - c) / a;
+#pragma unroll
   for (int i = 0; i < 3; i++)
+#pragma unroll
     for (int j = 0; j < 3; j++) {
       const double id = (i == j) ? 1.0 : 0.0, nn = n[i] * n[j];
       R[3 * i + j] = c * id + (1.0 - c) * nn + s * ah[3 * i + j];

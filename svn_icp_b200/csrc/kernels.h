@@ -128,6 +128,7 @@ struct SteinArgs {
   unsigned long long *kept_hist;  // [I] candidates kept by the prune pass per iteration (statistics)
   double *prep_scratch_d;         // [sm_count][12] per-CTA partial sums of the fused tail kernel
   int *prep_scratch_i;            // [PRUNE_BINS + 3] envelope / alpha / beta / NaN flag maxima (bit patterns)
+  double *stamps;                 // [8] globaltimer stamps of k_tail's phases (tuning aid; null = off)
   int sm_count;
 };
 // SVN-ICP class, Stein phase (tail2.cu): k_head = early-stop decision + history row + exact median bandwidth (cooperative,

@@ -300,6 +300,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = a.P;
+  // phase stamps (ns, tuning aid): CTA 0 stamps 0..3, the last CTA 4..5
+#define TL_STAMP(k) do { if (a.stamps && tid == 0) a.stamps[k] = (double)global_timer_ns(); } while (0)
+  if (blockIdx.x == 0) TL_STAMP(0);
   const int TJ = 32 * JQ;                                   // records per tile
   const size_t tile_bytes = (size_t)TJ * REC * sizeof(double);
   uint64_t *full = reinterpret_cast<uint64_t *>(s_dyn + (size_t)stages * tile_bytes);
@@ -316,6 +319,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
   const double *rec = a.rec + (size_t)(it & 1) * a.rec_stride;
   const size_t nxt_off = (size_t)((it + 1) & 1) * a.rec_stride;
   const double h = c->bandwidth;
+  if (blockIdx.x == 0) TL_STAMP(1);
 
   if (warp == TL_WARPS) {
     // ---------------- producer warp: AoS record tiles, one bulk copy each ----------------
@@ -430,18 +434,30 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
     }
   }
   __syncthreads();
+  if (blockIdx.x == 0) TL_STAMP(2);
   if (P >= 2 && !a.svn_full_grad && tid == 0) {
-    double A[36], Inv[36];
+    double A0[36];
+#pragma unroll
     for (int r = 0; r < 6; r++)
+#pragma unroll
       for (int cc = r; cc < 6; cc++) {
         double s = 0.0;
         for (int w = 0; w < JQ; w++) s += s_Hbar[w][tri(r, cc)];
-        A[6 * r + cc] = s / (double)P;  // :85 mean over particles
-        A[6 * cc + r] = A[6 * r + cc];
+        A0[6 * r + cc] = s / (double)P;  // :85 mean over particles
+        A0[6 * cc + r] = A0[6 * r + cc];
       }
-    for (int q = 0; q < 36; q++) Inv[q] = (q % 7 == 0) ? 1.0 : 0.0;
-    lu_solve6(A, Inv, 6);  // :225
-    for (int q = 0; q < 36; q++) s_Hinv[q] = Inv[q];
+    // :225 inverse, column by column (each solve register resident; the pivot sequence is the same for every column)
+#pragma unroll
+    for (int col = 0; col < 6; col++) {
+      double A[36], e[6];
+#pragma unroll
+      for (int q = 0; q < 36; q++) A[q] = A0[q];
+#pragma unroll
+      for (int q = 0; q < 6; q++) e[q] = (q == col) ? 1.0 : 0.0;
+      lu_solve6_reg(A, e);
+#pragma unroll
+      for (int q = 0; q < 6; q++) s_Hinv[6 * q + col] = e[q];
+    }
   }
   if (P >= 2 && !a.svn_full_grad) __syncthreads();
 
@@ -459,26 +475,32 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
       if (P < 2) {  // SVNICP.cpp:88-89
         double A[36];
         const double *r = rec + (size_t)p * REC;
+#pragma unroll
         for (int rr = 0; rr < 6; rr++)
+#pragma unroll
           for (int cc = rr; cc < 6; cc++) { A[6 * rr + cc] = __ldcg(r + REC_H + tri(rr, cc)); A[6 * cc + rr] = A[6 * rr + cc]; }
+#pragma unroll
         for (int q = 0; q < 6; q++) d[q] = __ldcg(r + REC_B + q);
-        lu_solve6(A, d, 1);
+        lu_solve6_reg(A, d);
         for (int q = 0; q < 6; q++) d[q] = -d[q];
       } else if (a.svn_full_grad) {
         double A[36];
+#pragma unroll
         for (int rr = 0; rr < 6; rr++)
+#pragma unroll
           for (int cc = rr; cc < 6; cc++) {
             double sum = 0.0;
             for (int w = 0; w < JQ; w++) sum += s_part[ii * JQ + w][tri(rr, cc)];
             A[6 * rr + cc] = sum / (double)P;
             A[6 * cc + rr] = A[6 * rr + cc];
           }
+#pragma unroll
         for (int q = 0; q < 6; q++) {
           double sum = 0.0;
           for (int w = 0; w < JQ; w++) sum += s_part[ii * JQ + w][21 + q];
           d[q] = sum / (double)P;
         }
-        lu_solve6(A, d, 1);  // :250 (the reference forms the explicit inverse; tolerance-level difference)
+        lu_solve6_reg(A, d);  // :250 (the reference forms the explicit inverse; tolerance-level difference)
         for (int q = 0; q < 6; q++) d[q] = a.lr * d[q];
       } else {
         double gs[6], kn[6], ks = 0.0;
@@ -552,6 +574,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
       for (int k = 0; k < 12; k++) s_xf[ii][k] = xfd[k];
   }
   __syncthreads();
+  if (blockIdx.x == 0) TL_STAMP(3);
   // per-CTA partial of the centre transform, fixed order; then the ticket: the last CTA publishes
   if (tid < 12) {
     double s = 0.0;
@@ -564,6 +587,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
   __syncthreads();
   if (!s_flag[0]) return;
   __threadfence();
+  TL_STAMP(4);
 
   // ---------------- last CTA: exact-pruning ball of the local slice for the next iteration (as k_prep) ----------------
   if (tid < 12) {
@@ -623,6 +647,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
     c->tail_ticket = 0u;
     c->iter = it + 1;
   }
+  TL_STAMP(5);
+#undef TL_STAMP
   // every CTA fenced its peer stores before taking its ticket: the new x of the whole slice is out -> tell the peers
   if (pt.n_ranks > 1 && tid < pt.n_ranks && tid != pt.rank) {
     __threadfence_system();
@@ -664,7 +690,7 @@ void tail_shape(int P_l, int sm_count, int *NI, int *JQ, int *stages, size_t *sm
   const int jq = TL_WARPS / ni;
   const size_t tile = (size_t)32 * jq * REC * sizeof(double);
   int s = (int)((150 * 1024) / tile);
-  if (s > 4) s = 4;
+  if (s > 12) s = 12;
   if (s < 1) s = 1;
   size_t bytes = (size_t)s * tile;
   if (bytes < (size_t)2 * TL_ENV_CHUNK * sizeof(float)) bytes = (size_t)2 * TL_ENV_CHUNK * sizeof(float);
