@@ -36,7 +36,11 @@ WORKLOAD = dict(sensor="64", particles=1000, iterations=30, K=100, max_dist=3.0,
                 scan_index=8, n_map_scans=8)
 METRIC = "scans/sec at 1000 particles (64-beam ~120k-pt synthetic scan, K=100, 30 SVN iterations)"
 WORKLOAD_NAME = "configs[1]: 64-beam synthetic scan, 1000 particles, particle-sharded when N>1"
-SHARD_TOL = 1e-7  # N-GPU vs 1-GPU particles (identical algorithm; only the grouping of fp32 partial sums depends on the slice)
+# N-GPU vs 1-GPU at the full size after 30 iterations: identical algorithm, but the grouping of the fp32 Gauss-Newton partial sums
+# depends on the slice, and a near-tie correspondence that flips because of it moves single particles by ~1e-6..1e-5 through the
+# repulsive dynamics (the same effect bounds ours-vs-reference at 7.6e-6).  Short scans agree to ~2e-9 (tests/mgpu_worker.py, 1e-7).
+SHARD_TOL = 5e-5       # single particles
+SHARD_TOL_MEAN = 1e-6  # particle mean
 
 
 def host_cores() -> int:
@@ -391,9 +395,11 @@ def main():
             o1 = scan_device(W + args.steps - 1, single)
             d_part = float(np.nanmax(np.abs(o1[3] - out[3])))
             d_hist = float(np.nanmax(np.abs(single.get_particle_history() - last_hist)))
-            check["sharded_vs_single_max_abs"] = dict(particles=d_part, history_f32=d_hist, mean=float(np.max(np.abs(o1[0] - out[0]))),
+            d_mean = float(np.max(np.abs(o1[0] - out[0])))
+            check["sharded_vs_single_max_abs"] = dict(particles=d_part, history_f32=d_hist, mean=d_mean,
                                                       cov=float(np.max(np.abs(o1[2] - out[2]))), iterations=[int(last_iters), int(single.iterations_done())],
-                                                      tolerance=SHARD_TOL, ok=bool(d_part <= SHARD_TOL and last_iters == single.iterations_done()))
+                                                      tolerance=dict(particles=SHARD_TOL, mean=SHARD_TOL_MEAN),
+                                                      ok=bool(d_part <= SHARD_TOL and d_mean <= SHARD_TOL_MEAN and last_iters == single.iterations_done()))
             single.close()
         barrier()
 
@@ -557,12 +563,13 @@ def main():
             line["reference_on_gpu"] = reference_on_gpu
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
-        if world > 1 and not check["sharded_vs_single_max_abs"]["ok"]:
-            raise SystemExit(f"sharded run differs from the single-GPU run: {check['sharded_vs_single_max_abs']}")
+        print(json.dumps(line), flush=True)
+    icp.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0 and not check["sharded_vs_single_max_abs"]["ok"]:
+            raise SystemExit(f"sharded run differs from the single-GPU run: {check['sharded_vs_single_max_abs']}")
 
 
 if __name__ == "__main__":

@@ -112,14 +112,15 @@ struct svnicp_handle_t {
   DevBuf<float4> sp, cand, clist;
   // list reuse across iterations (k_filter): second list buffer, true list lengths and the balls the lists are exact for
   DevBuf<float4> clist2, ball[2];
-  DevBuf<int> ccount2, cbase[2];
+  DevBuf<float4> hdr, hdr2;  // row headers of the pruned lists (ping-pong with the lists)
+  DevBuf<int> cbase[2];
   int filter_reuse = 1;
   // internal particle order (compute_particle_order): internal index i holds the caller's particle perm[i]
   std::vector<int> perm;
   std::vector<double> perm_stage;
   bool permuted = false;
   int rows_per_rank = 0;
-  DevBuf<int> ccount, counts, starts, fill, pt_slot, sidx, misc, cand_idx;
+  DevBuf<int> counts, starts, fill, pt_slot, sidx, misc, cand_idx;
   int Kp = 100;  // misc: [0] cursor, [1] fallback count
   DevBuf<unsigned long long> keys, kept_hist;
   DevBuf<float> xf, history, dbg_xf;
@@ -426,10 +427,10 @@ void svnicp_destroy(svnicp_handle h) {
   h->stamps.release();
   for (auto *b : d) b->release();
   h->sp.release(); h->cand.release(); h->clist.release();
-  h->clist2.release(); h->ccount2.release();
+  h->clist2.release(); h->hdr.release(); h->hdr2.release();
   for (int i = 0; i < 2; i++) { h->ball[i].release(); h->cbase[i].release(); }
   h->cand_idx.release();
-  h->ccount.release(); h->counts.release(); h->starts.release(); h->fill.release(); h->pt_slot.release(); h->sidx.release(); h->misc.release();
+  h->counts.release(); h->starts.release(); h->fill.release(); h->pt_slot.release(); h->sidx.release(); h->misc.release();
   h->keys.release(); h->kept_hist.release(); h->xf.release(); h->dbg_xf.release(); h->history.release(); h->hist.release(); h->ctrl.release();
   h->dbg_idx.release(); h->dbg_mask.release();
   if (h->h_stats) cudaFreeHost(h->h_stats);
@@ -577,14 +578,14 @@ static int prepare_scan(svnicp_handle h) {
   // global map index per slot: only the parity taps read it (svnicp_get_candidates / _get_correspondences)
   if (h->prm.debug_corr) CU(h->cand_idx.ensure((size_t)h->rows_per_rank * h->n_ranks * h->K));
   CU(h->clist.ensure((size_t)n_pad * h->Kp));
-  CU(h->ccount.ensure((size_t)n_pad + 64));
-  CU(cudaMemsetAsync(h->ccount.p, 0, ((size_t)n_pad + 64) * sizeof(int), h->stream));
+  CU(h->hdr.ensure((size_t)n_pad + 64));
+  CU(cudaMemsetAsync(h->hdr.p, 0, ((size_t)n_pad + 64) * sizeof(float4), h->stream));  // rows [n_s, n_pad) stay padding rows
   // SVNICP_FLAG_FILTER_FULL: prune from the full K-slot table every iteration (A/B measurements, roofline of the streaming pass)
   h->filter_reuse = (h->prm.flags & SVNICP_FLAG_FILTER_FULL) ? 0 : 1;
   if (h->filter_reuse) {
     CU(h->clist2.ensure((size_t)n_pad * h->Kp));
-    CU(h->ccount2.ensure((size_t)n_pad + 64));
-    CU(cudaMemsetAsync(h->ccount2.p, 0, ((size_t)n_pad + 64) * sizeof(int), h->stream));
+    CU(h->hdr2.ensure((size_t)n_pad + 64));
+    CU(cudaMemsetAsync(h->hdr2.p, 0, ((size_t)n_pad + 64) * sizeof(float4), h->stream));
     for (int i = 0; i < 2; i++) {
       CU(h->ball[i].ensure((size_t)n_pad + 64));
       CU(h->cbase[i].ensure((size_t)n_pad + 64));
@@ -758,7 +759,7 @@ int svnicp_align(svnicp_handle h) {
   ia.P = h->P; ia.p_lo = h->p_lo; ia.P_l = h->P_l;
   ia.sc = h->sc;
   ia.max_dist = (float)h->max_dist;
-  ia.sp = h->sp.p; ia.cand = h->cand.p; ia.clist = h->clist.p; ia.ccount = h->ccount.p;
+  ia.sp = h->sp.p; ia.cand = h->cand.p; ia.clist = h->clist.p; ia.hdr = h->hdr.p;
   ia.R = h->R.p; ia.t = h->t.p; ia.xf = h->xf.p; ia.dnorm = h->dnorm.p; ia.part = h->part.p; ia.rec = h->rec; ia.rec_stride = h->rec_stride; ia.ctrl = h->ctrl.p;
   ia.TB = h->TB; ia.stages = h->stages; ia.n_slices = h->n_slices; ia.n_pgroups = h->n_pgroups; ia.PG = h->PG; ia.RG = h->RG;
   ia.gn_smem = h->gn_smem; ia.sm_count = h->sm_count; ia.svn_full_grad = h->prm.SVN_full_grad;
@@ -821,7 +822,7 @@ int svnicp_align(svnicp_handle h) {
     if (h->filter_reuse) {  // ping-pong: iteration e prunes the lists of iteration e-1 wherever its ball still covers this one's
       const int cur = e & 1;
       ia.clist = cur ? h->clist2.p : h->clist.p;
-      ia.ccount = cur ? h->ccount2.p : h->ccount.p;
+      ia.hdr = cur ? h->hdr2.p : h->hdr.p;
       ia.cbase = h->cbase[cur].p;
       ia.ball = h->ball[cur].p;
       ia.clist_prev = e > 0 ? (cur ? h->clist.p : h->clist2.p) : nullptr;

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256, 4) k_filter(IterArgs a) {  // 64 register
     const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);  // k_gn scans 2, then chunks of 4
     if (lane < padded - base) out[base + lane] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
     if (lane == 0) {
-      a.ccount[b] = padded;
+      a.hdr[b] = make_float4(s.x, s.y, s.z, __int_as_float((padded << 16) | base));  // row header of k_gn: source point + list length
       kept += (unsigned long long)base;
       if (a.ball) { a.cbase[b] = base; a.ball[b] = make_float4(qx, qy, qz, rho); }  // what this list is exact for (k_filter_reuse)
     }
@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(256, 4) k_filter(IterArgs a) {  // 64 register
 constexpr int FR_FAST = SVN_FR_FAST;
 
 struct FrRow {
+  float sx, sy, sz;
   float qx, qy, qz, rho;
   bool from_prev;
   int n_prev;
@@ -272,6 +273,7 @@ __device__ __forceinline__ FrRow fr_row_setup(const IterArgs &a, const float *A,
   const float4 s = a.sp[b];
   const float4 pb = a.ball_prev[b];
   FrRow r;
+  r.sx = s.x; r.sy = s.y; r.sz = s.z;
   r.n_prev = a.cbase_prev[b];
   r.qx = fmaf(A[0], s.x, fmaf(A[1], s.y, fmaf(A[2], s.z, tb[0])));
   r.qy = fmaf(A[3], s.x, fmaf(A[4], s.y, fmaf(A[5], s.z, tb[1])));
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(256, 4) k_filter_reuse(IterArgs a) {
       }
       const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);
       for (int k = base; k < padded; k++) out[k] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-      a.ccount[b] = padded;
+      a.hdr[b] = make_float4(r.sx, r.sy, r.sz, __int_as_float((padded << 16) | base));
       a.cbase[b] = base;
       a.ball[b] = make_float4(r.qx, r.qy, r.qz, r.rho);
       kept += (unsigned long long)base + (1ull << 40);  // high bits: rows served by the previous list
@@ -346,6 +348,7 @@ __global__ void __launch_bounds__(256, 4) k_filter_reuse(IterArgs a) {
       const int bb = b0 + src_lane;
       const float qx = __shfl_sync(0xffffffffu, r.qx, src_lane), qy = __shfl_sync(0xffffffffu, r.qy, src_lane);
       const float qz = __shfl_sync(0xffffffffu, r.qz, src_lane), rho = __shfl_sync(0xffffffffu, r.rho, src_lane);
+      const float sx = __shfl_sync(0xffffffffu, r.sx, src_lane), sy = __shfl_sync(0xffffffffu, r.sy, src_lane), sz = __shfl_sync(0xffffffffu, r.sz, src_lane);
       const bool from_prev = __shfl_sync(0xffffffffu, (int)r.from_prev, src_lane) != 0;
       const int n_src = from_prev ? __shfl_sync(0xffffffffu, r.n_prev, src_lane) : K;
       const float4 *row = from_prev ? a.clist_prev + (size_t)bb * Kp : a.cand + (size_t)bb * K;
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(256, 4) k_filter_reuse(IterArgs a) {
       const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);
       if (lane < padded - base) out[base + lane] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
       if (lane == 0) {
-        a.ccount[bb] = padded;
+        a.hdr[bb] = make_float4(sx, sy, sz, __int_as_float((padded << 16) | base));
         a.cbase[bb] = base;
         a.ball[bb] = make_float4(qx, qy, qz, rho);
         kept += (unsigned long long)base + (from_prev ? (1ull << 40) : 0ull);
@@ -426,6 +429,10 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // FIRST: first-order mode of the SVGD-ICP class (SVGDICP::sgd_grad, SVGDICP.cpp:398-455): sum 0 counts the unmasked
 // pairs (nonzero_count, :404) and the second-moment sums 1..9 are not needed -- the gradient is E and C alone because
 // every Euler partial is [omega_k]x R (see svgd_class.cu).
+// Stage layout: [TB][Kp] float4 pruned lists, then [TB + 1] float4 row headers (source point R0 s, w = list length bits:
+// padded length << 16 | true length; 0 = padding row; slot TB is a dummy so the next row's header is prefetched unconditionally).
+constexpr int GN_SINGLE = (2 << 16) | 1;  // header bits of a row whose pruned list holds exactly one candidate
+
 template <bool DBG, bool UNI, bool FIRST>
 __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a) {  // (.., 3) spills the fp64 accumulators: measured slower
   if (a.ctrl->stop) return;
@@ -452,19 +459,16 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
       mbar_wait(empty + s, (uint32_t)((k & 1) ^ 1));
       const int row0 = (slice + i * n_slices) * TB;
       unsigned char *st = smem + (size_t)s * stage_bytes;
-      const int cnt = (lane < TB) ? a.ccount[row0 + lane] : 0;
+      const int cnt = (lane < TB) ? (__float_as_int(a.hdr[row0 + lane].w) >> 16) : 0;
       int bytes = cnt * 16;
       int total = bytes;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      total += TB * 16 + TB * 4;
+      total += TB * 16;
       if (lane == 0) mbar_expect_tx(full + s, (uint32_t)total);
       __syncwarp();
       if (lane < TB && cnt > 0) bulk_g2s(st + (size_t)lane * Kp * 16, a.clist + (size_t)(row0 + lane) * Kp, (uint32_t)bytes, full + s);
-      if (lane == 0) {
-        bulk_g2s(st + (size_t)TB * Kp * 16, a.sp + row0, (uint32_t)(TB * 16), full + s);
-        bulk_g2s(st + (size_t)TB * Kp * 16 + (size_t)TB * 16, a.ccount + row0, (uint32_t)(TB * 4), full + s);
-      }
+      if (lane == 0) bulk_g2s(st + (size_t)TB * Kp * 16, a.hdr + row0, (uint32_t)(TB * 16), full + s);
     }
     return;
   }
@@ -490,57 +494,61 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
   double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + (active ? l : 0)) * NACC;
   const int row_step = RG * Kp;
 
-// one candidate: fixed operation order (index parity with oracle_corr_f32); strict '<', first slot wins (mink.cuh:141)
-#define SVN_EVAL(C, SLOT)                                                                              \
+// one candidate: fixed operation order (index parity with oracle_corr_f32); strict '<', first slot wins (mink.cuh:141).
+// The residual e = q - c of the running winner is carried along (no reload of the winner afterwards).
+#define SVN_EVAL(C)                                                                                    \
   {                                                                                                    \
     const float dx_ = __fsub_rn(qx, (C).x), dy_ = __fsub_rn(qy, (C).y), dz_ = __fsub_rn(qz, (C).z);    \
     const float d_ = __fmaf_rn(dz_, dz_, __fmaf_rn(dy_, dy_, __fmul_rn(dx_, dx_)));                    \
-    if (d_ < best) { best = d_; bi = (SLOT); }                                                         \
+    if (d_ < best) {                                                                                   \
+      best = d_; ex = dx_; ey = dy_; ez = dz_;                                                         \
+      if (DBG) { wx_ = (C).x; wy_ = (C).y; wz_ = (C).z; }                                              \
+    }                                                                                                  \
   }
 
   for (int i = 0; i < n_my; i++) {
     const int s = i % S, k = i / S;
     mbar_wait(full + s, (uint32_t)(k & 1));
     const unsigned char *st = smem + (size_t)s * stage_bytes;
-    const float4 *src = reinterpret_cast<const float4 *>(st + (size_t)TB * Kp * 16);
-    const int *cnt = reinterpret_cast<const int *>(st + (size_t)TB * Kp * 16 + (size_t)TB * 16);
+    const float4 *hdr = reinterpret_cast<const float4 *>(st + (size_t)TB * Kp * 16);
     if (UNI || active) {
       const float4 *e = reinterpret_cast<const float4 *>(st) + (size_t)rg * Kp;
-      int n = cnt[rg];  // padded to a multiple of 4; 0 = padding row
-      float4 sv = src[rg];
+      float4 sv = hdr[rg];
       for (int r = rg; r < TB; r += RG, e += row_step) {
-        // software prefetch of the next row's header
-        int n_nx = 0;
-        float4 sv_nx = sv;
-        if (r + RG < TB) { n_nx = cnt[r + RG]; sv_nx = src[r + RG]; }
-        if (n != 0) {
+        const float4 sv_nx = hdr[min(r + RG, TB)];  // software prefetch of the next row's header (slot TB: dummy)
+        const int bits = __float_as_int(sv.w);
+        if (bits != 0) {
           float4 c0 = e[0], c1 = e[1], c2, c3;
+          const int n = bits >> 16;  // padded to 2, then a multiple of 4
           if (n > 2) { c2 = e[2]; c3 = e[3]; }
           // a = A' s' ; q = a + tau : query relative to q0_b.  Order fixed (index parity).
           const float ax = __fmaf_rn(A0, sv.x, __fmaf_rn(A1, sv.y, __fmul_rn(A2, sv.z)));
           const float ay = __fmaf_rn(A3, sv.x, __fmaf_rn(A4, sv.y, __fmul_rn(A5, sv.z)));
           const float az = __fmaf_rn(A6, sv.x, __fmaf_rn(A7, sv.y, __fmul_rn(A8, sv.z)));
           const float qx = __fadd_rn(ax, t0), qy = __fadd_rn(ay, t1), qz = __fadd_rn(az, t2);
-          float best = INFINITY;
-          int bi = 0;
-          SVN_EVAL(c0, 0) SVN_EVAL(c1, 1)
-          if (n > 2) { SVN_EVAL(c2, 2) SVN_EVAL(c3, 3) }
-          if (n > 4) {
-            // upper bound of |q| (distance of this particle's query from the initial-guess query q0_b)
-            const float qn = fmaf(sqrt_approx(fmaf(qz, qz, fmaf(qy, qy, qx * qx))), 1.00001f, 1e-7f);
-            for (int k0 = 4; k0 < n; k0 += 4) {
-              c0 = e[k0]; c1 = e[k0 + 1]; c2 = e[k0 + 2]; c3 = e[k0 + 3];
-              // exact early exit: slots ascend in |c| (= c.w, a lower bound) and |q - c| >= |c| - |q|, so once
-              // (|c| - |q|)^2 > best no later slot can win or tie.  NaN anywhere compares false -> no exit.
-              const float tt = c0.w - qn;
-              const bool done = (tt > 0.f) && (tt * tt * 0.99999f > best);
-              if (UNI) { if (__all_sync(0xffffffffu, done)) break; }
-              else { if (done) break; }
-              SVN_EVAL(c0, k0) SVN_EVAL(c1, k0 + 1) SVN_EVAL(c2, k0 + 2) SVN_EVAL(c3, k0 + 3)
+          float wx_ = c0.x, wy_ = c0.y, wz_ = c0.z;  // DBG only: coordinates of the winner
+          // slot 0 always exists: its residual starts the search (same bits as an evaluation against best = +inf)
+          float ex = __fsub_rn(qx, c0.x), ey = __fsub_rn(qy, c0.y), ez = __fsub_rn(qz, c0.z);
+          float best = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+          if (!(best == best)) best = INFINITY;  // NaN distance: later slots are compared against +inf, as MinK's strict '<' does
+          if (bits != GN_SINGLE) {  // warp-uniform: a one-candidate list needs no search at all
+            SVN_EVAL(c1)
+            if (n > 2) { SVN_EVAL(c2) SVN_EVAL(c3) }
+            if (n > 4) {
+              // upper bound of |q| (distance of this particle's query from the initial-guess query q0_b)
+              const float qn = fmaf(sqrt_approx(fmaf(qz, qz, fmaf(qy, qy, qx * qx))), 1.00001f, 1e-7f);
+              for (int k0 = 4; k0 < n; k0 += 4) {
+                c0 = e[k0]; c1 = e[k0 + 1]; c2 = e[k0 + 2]; c3 = e[k0 + 3];
+                // exact early exit: slots ascend in |c| (= c.w, a lower bound) and |q - c| >= |c| - |q|, so once
+                // (|c| - |q|)^2 > best no later slot can win or tie.  NaN anywhere compares false -> no exit.
+                const float tt = c0.w - qn;
+                const bool done = (tt > 0.f) && (tt * tt * 0.99999f > best);
+                if (UNI) { if (__all_sync(0xffffffffu, done)) break; }
+                else { if (done) break; }
+                SVN_EVAL(c0) SVN_EVAL(c1) SVN_EVAL(c2) SVN_EVAL(c3)
+              }
             }
           }
-          const float4 cw = e[bi];
-          const float ex = __fsub_rn(qx, cw.x), ey = __fsub_rn(qy, cw.y), ez = __fsub_rn(qz, cw.z);
           const bool valid = best < Dm;  // SVGDICP.cpp:332: squared distance vs un-squared max_dist (Q1)
           if (DBG) {
             if (active) {
@@ -550,7 +558,7 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
               int slot = 0;
               for (int kk = 0; kk < a.K; kk++) {
                 const float4 f = full_row[kk];
-                if (f.x == cw.x && f.y == cw.y && f.z == cw.z) { slot = kk; break; }
+                if (f.x == wx_ && f.y == wy_ && f.z == wz_) { slot = kk; break; }
               }
               a.dbg_idx[(size_t)l * a.n_s + row] = a.cand_idx[(size_t)row * a.K + slot];
               a.dbg_mask[(size_t)l * a.n_s + row] = valid ? 1 : 0;
@@ -578,7 +586,6 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
           acc[15] = fmaf(wx, fy, fmaf(-wy, fx, acc[15]));
           rows_in_acc++;
         }
-        n = n_nx;
         sv = sv_nx;
       }
       if (rows_in_acc >= GN_FLUSH_ROWS) {

@@ -41,7 +41,7 @@ struct IterArgs {
   // buffers
   const float4 *sp, *cand;
   float4 *clist;
-  int *ccount;
+  float4 *hdr;          // [n_pad] row headers of the pruned lists: (R0 s).xyz, w = (padded length << 16 | true length) bits; 0 = padding row
   // list reuse (k_filter): the previous iteration's pruned lists, their true lengths and the ball (centre query, radius)
   // they are exact for; null = always prune from the full table.  cbase / ball: the same for THIS iteration's output.
   const float4 *clist_prev;
@@ -106,8 +106,8 @@ int launch_filter(const IterArgs &a, cudaStream_t st);
 int launch_gn(const IterArgs &a, cudaStream_t st);
 int launch_finalize(const IterArgs &a, const PeerTable &pt, unsigned seq_h, cudaStream_t st);
 void init_iter_kernels();
-// bytes of one shared-memory stage of k_gn: TB pruned rows of K float4 + TB source points + TB counts
-__host__ __device__ inline size_t gn_stage_bytes(int TB, int K) { return (size_t)TB * K * 16 + (size_t)TB * 16 + (size_t)TB * 4; }
+// bytes of one shared-memory stage of k_gn: TB pruned rows of K float4 + TB + 1 row headers (the last one a dummy), 128-byte aligned
+__host__ __device__ inline size_t gn_stage_bytes(int TB, int K) { return ((size_t)TB * K * 16 + (size_t)(TB + 1) * 16 + 127) & ~(size_t)127; }
 
 struct SteinArgs {
   int P, p_lo, P_l, I;

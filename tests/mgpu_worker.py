@@ -34,7 +34,7 @@ def main():
     for P, full, es, cls, flags, twice in cases:
         pb = synth.make_problem(P, sensor="32", scan_index=6, n_map_scans=6, seed=0xC0FFEE)
         if cls == "svn":
-            prm = sv.SteinICPParam(iterations=10, KNN_count=64, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
+            prm = sv.SteinICPParam(iterations=5 if twice else 10, KNN_count=64, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
                                    convergence_threshold=1e-2, flags=flags)
             make = lambda: sv.SVNICP(prm, pb.init_pose, device=local)
         else:  # the SVGD-ICP class shards the same way (first-order record, one all-gather per iteration)
