@@ -176,6 +176,24 @@ int svnicp_get_tail_stamps(svnicp_handle h, double out8[8]);
 int svnicp_get_launch_count(svnicp_handle h, int64_t *out);
 
 /* ---------------------------------------------------------------------------------------------
+ * Throughput mode: S independent odometry streams on one GPU (BASELINE.json configs[3]; no reference counterpart -- the
+ * reference runs one SVNICP instance per node process).  A batch owns one SVN-ICP handle per stream; use
+ * svnicp_batch_stream(b, s) with svnicp_add_cloud / svnicp_set_initial_mean / the getters exactly as for a single handle
+ * (do not destroy it, do not call svnicp_set_stream on it), and svnicp_batch_align instead of svnicp_align: it enqueues the
+ * scans of all streams iteration by iteration so that they overlap on the GPU, then waits for all of them.  Each stream's
+ * result is bit-identical to svnicp_align on that handle.  init_pose: [S][6][P] or NULL.  states: [S] SteinICPState or a
+ * negative status per stream; the return value is SVNICP_ALIGN_SUCCESS or the last negative status.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct svnicp_batch_t *svnicp_batch;
+int svnicp_batch_create(svnicp_batch *out, const svnicp_params *params, int n_streams, int particle_count, const double *init_pose,
+                        int device);
+void svnicp_batch_destroy(svnicp_batch b);
+const char *svnicp_batch_last_error(svnicp_batch b);
+int svnicp_batch_size(svnicp_batch b);
+svnicp_handle svnicp_batch_stream(svnicp_batch b, int s);
+int svnicp_batch_align(svnicp_batch b, int32_t *states);
+
+/* ---------------------------------------------------------------------------------------------
  * Device-resident local map: svnicp::VoxelHashMap (svn-icp/include/core/VoxelHashMap.h:28-72,
  * src/core/VoxelHashMap.cpp:22-101) kept in HBM, so the target cloud of svnicp_add_cloud
  * (target_on_device = 1) never crosses PCIe (the reference rebuilds and re-uploads it every scan,

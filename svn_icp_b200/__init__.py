@@ -89,6 +89,7 @@ EXPORTS = [
     "svnicp_map_download", "svnicp_map_size",
     "svnicp_pre_create", "svnicp_pre_destroy", "svnicp_pre_last_error", "svnicp_pre_crop", "svnicp_pre_downsample_uniform",
     "svnicp_pre_to_f64", "svnicp_pre_download", "svnicp_pre_deskew", "svnicp_pose_compose",
+    "svnicp_batch_create", "svnicp_batch_destroy", "svnicp_batch_last_error", "svnicp_batch_size", "svnicp_batch_stream", "svnicp_batch_align",
 ]
 
 
@@ -105,7 +106,7 @@ def load_library() -> C.CDLL:
         for name in EXPORTS:
             fn = getattr(lib, name)
             if name not in ("svnicp_last_error", "svnicp_destroy", "svnicp_default_params", "svnicp_map_last_error", "svnicp_map_destroy",
-                            "svnicp_pre_last_error", "svnicp_pre_destroy"):
+                            "svnicp_pre_last_error", "svnicp_pre_destroy", "svnicp_batch_destroy", "svnicp_batch_last_error", "svnicp_batch_stream"):
                 fn.restype = C.c_int
         lib.svnicp_pre_destroy.restype = None
         lib.svnicp_pre_destroy.argtypes = [C.c_void_p]
@@ -118,6 +119,9 @@ def load_library() -> C.CDLL:
         lib.svnicp_map_last_error.restype = C.c_char_p
         lib.svnicp_map_last_error.argtypes = [C.c_void_p]
         lib.svnicp_default_params.restype = None
+        lib.svnicp_batch_destroy.restype = None
+        lib.svnicp_batch_last_error.restype = C.c_char_p
+        lib.svnicp_batch_stream.restype = C.c_void_p
         V, I, L, D = C.c_void_p, C.c_int, C.c_int64, C.c_double
         for name, at in _ARGTYPES(V, I, L, D).items():
             getattr(lib, name).argtypes = at
@@ -145,6 +149,10 @@ def _ARGTYPES(V, I, L, D):
         "svnicp_pre_create": [V, L, I], "svnicp_pre_crop": [V, V, L, I, D, D, V, V, V],
         "svnicp_pre_downsample_uniform": [V, V, L, I, D, V, V], "svnicp_pre_to_f64": [V, V, L, V], "svnicp_pre_download": [V, V, L, V],
         "svnicp_pre_deskew": [V, V, L, I, V, I, I, V, V, V, V, V, V], "svnicp_pose_compose": [V, V, V, V, V],
+        "svnicp_batch_create": [V, V, I, I, V, I], "svnicp_batch_destroy": [V], "svnicp_batch_last_error": [V], "svnicp_batch_size": [V],
+        "svnicp_batch_stream": [V, I], "svnicp_batch_align": [V, V],
+        "svnicp_destroy": [V], "svnicp_last_error": [V], "svnicp_map_destroy": [V], "svnicp_map_last_error": [V],
+        "svnicp_pre_destroy": [V], "svnicp_pre_last_error": [V],
     }
 
 
@@ -182,6 +190,20 @@ def nccl_unique_id() -> bytes:
     return buf.raw
 
 
+def _c_params(lib, param: SteinICPParam, opt: ParticleWeightOpt | None = None) -> _CParams:
+    cp = _CParams()
+    lib.svnicp_default_params(C.byref(cp))
+    for f in ("iterations", "batch_size", "convergence_steps", "KNN_count", "flags", "gn_stages", "gn_smem_kb"):
+        setattr(cp, f, int(getattr(param, f)))
+    for f in ("use_minibatch", "normalize_cloud", "check_early_stop", "SVN_full_grad", "debug_corr"):
+        setattr(cp, f, int(bool(getattr(param, f))))
+    for f in ("lr", "max_dist", "convergence_threshold", "grid_cell"):
+        setattr(cp, f, float(getattr(param, f)))
+    cp.optimizer = param.optimizer.encode()[:15]
+    cp.use_weight_mean = int(bool(opt.use_weight_mean)) if opt else 0
+    return cp
+
+
 class SVNICP:
     """Drop-in for svnicp::SVNICP.  init_pose: [6, P] (or the reference's [6, P, 1])."""
 
@@ -193,16 +215,7 @@ class SVNICP:
         init_pose = _f64(init_pose).reshape(6, -1)
         self.particle_size = init_pose.shape[1]
         self.param = dataclasses.replace(param)
-        cp = _CParams()
-        self._lib.svnicp_default_params(C.byref(cp))
-        for f in ("iterations", "batch_size", "convergence_steps", "KNN_count", "flags", "gn_stages", "gn_smem_kb"):
-            setattr(cp, f, int(getattr(param, f)))
-        for f in ("use_minibatch", "normalize_cloud", "check_early_stop", "SVN_full_grad", "debug_corr"):
-            setattr(cp, f, int(bool(getattr(param, f))))
-        for f in ("lr", "max_dist", "convergence_threshold", "grid_cell"):
-            setattr(cp, f, float(getattr(param, f)))
-        cp.optimizer = param.optimizer.encode()[:15]
-        cp.use_weight_mean = int(bool(opt.use_weight_mean)) if opt else 0
+        cp = _c_params(self._lib, param, opt)
         rc = self._lib.svnicp_create(C.byref(self._h), C.byref(cp), C.c_int(self.particle_size), _p(init_pose),
                                      C.c_int(self.class_type), C.c_int(device))
         if rc != 0:
@@ -216,9 +229,18 @@ class SVNICP:
             raise SvnIcpError(f"{what} failed ({rc}): " + (self._lib.svnicp_last_error(self._h) or b"").decode())
         return rc
 
+    @classmethod
+    def _borrowed(cls, lib, handle: int, param: SteinICPParam, particle_size: int):
+        """A view of a handle owned by someone else (SVNICPBatch): same methods, close() does not destroy it."""
+        self = cls.__new__(cls)
+        self._lib, self._h, self._owned = lib, C.c_void_p(handle), False
+        self.param, self.particle_size, self.n_s = dataclasses.replace(param), particle_size, 0
+        return self
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            self._lib.svnicp_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._lib.svnicp_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -423,6 +445,45 @@ def pose_compose(R0, t0, mean6):
     if rc:
         raise SvnIcpError("pose_compose: invalid argument")
     return R, t
+
+
+class SVNICPBatch:
+    """Throughput mode (BASELINE.json configs[3]): S independent SVN-ICP streams on one GPU.  `streams[s]` is an SVNICP
+    bound to stream s (add_cloud / set_initial_mean / getters as usual); `stein_align()` runs the scans of all streams
+    interleaved so they overlap on the GPU and returns the per-stream SteinICPState list."""
+
+    def __init__(self, param: SteinICPParam, init_poses, device: int = -1):
+        self._lib = load_library()
+        self._b = C.c_void_p()
+        ip = _f64(init_poses)
+        assert ip.ndim == 3 and ip.shape[1] == 6, "init_poses: [S, 6, P]"
+        S, _, P = ip.shape
+        cp = _c_params(self._lib, param)
+        rc = self._lib.svnicp_batch_create(C.byref(self._b), C.byref(cp), C.c_int(S), C.c_int(P), _p(ip), C.c_int(device))
+        if rc != 0:
+            self._b = C.c_void_p()
+            raise SvnIcpError(f"svnicp_batch_create failed ({rc}): " + (self._lib.svnicp_last_error(None) or b"").decode())
+        self.streams = [SVNICP._borrowed(self._lib, self._lib.svnicp_batch_stream(self._b, C.c_int(s)), param, P) for s in range(S)]
+
+    def stein_align(self):
+        states = (C.c_int32 * len(self.streams))()
+        rc = self._lib.svnicp_batch_align(self._b, states)
+        if rc < 0:
+            raise SvnIcpError(f"batch stein_align failed ({rc}): " + (self._lib.svnicp_batch_last_error(self._b) or b"").decode())
+        return list(states)
+
+    def close(self):
+        if getattr(self, "_b", None) and self._b.value:
+            for s in self.streams:
+                s.close()
+            self._lib.svnicp_batch_destroy(self._b)
+            self._b = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class VoxelHashMap:

@@ -662,14 +662,31 @@ static int do_allgather(svnicp_handle h, int buf = 0) {
   return SVNICP_OK;
 }
 
-int svnicp_align(svnicp_handle h) {
-  if (!h) return SVNICP_ERR_INVALID;
+// One scan = begin (setup + head of the scan) -> step x iterations -> epilogue (enqueue) -> finish (synchronise, read back).
+// svnicp_align runs them back to back; svnicp_batch_align interleaves the steps of several handles so that their streams
+// overlap on the GPU (throughput mode).
+struct AlignState {
+  IterArgs ia;
+  SteinArgs sa;
+  SvgdArgs sv;
+  PeerTable pt;
+  bool svgd = false, overlap = false, realign = false, special = false, enqueue_done = false;
+  unsigned seq0 = 0;
+  int I = 0, e = 0;
+};
+#define ALIGN_LOCALS                                                                                                     \
+  IterArgs &ia = S.ia; SteinArgs &sa = S.sa; const SvgdArgs &sv = S.sv; PeerTable &pt = S.pt;                            \
+  const bool svgd = S.svgd, overlap = S.overlap; const unsigned seq0 = S.seq0; const int I = S.I;                        \
+  cudaStream_t st = h->stream, hs = h->head_stream;                                                                      \
+  (void)ia; (void)sa; (void)sv; (void)pt; (void)svgd; (void)overlap; (void)seq0; (void)I; (void)st; (void)hs;
+
+static int align_begin(svnicp_handle h, AlignState &S) {
   if (!h->have_cloud) return fail(h, SVNICP_ERR_INVALID, "stein_align before add_cloud");
   CU(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  const int I = h->prm.iterations;
+  const int I = S.I = h->prm.iterations;
   h->launches = 0;
-  const bool realign = h->aligned;  // stein_align again without a fresh add_cloud: continue from the current poses
+  const bool realign = S.realign = h->aligned;  // stein_align again without a fresh add_cloud: continue from the current poses
   if (h->shape_dirty) {
     const int rc = prepare_scan(h);
     if (rc) return rc;
@@ -697,11 +714,11 @@ int svnicp_align(svnicp_handle h) {
   CU(cudaMemsetAsync(h->history.p, 0, (size_t)(I > 0 ? I : 1) * 6 * h->P * sizeof(float), st));  // SVGDICP.cpp:172-174
   CU(cudaMemsetAsync(h->kept_hist.p, 0, ((size_t)I + 2) * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(h->misc.p, 0, 8 * sizeof(int), st));
-  const bool svgd = h->class_type == SVNICP_CLASS_SVGDICP;
+  const bool svgd = S.svgd = h->class_type == SVNICP_CLASS_SVGDICP;
   // A scan may be run again without a fresh add_cloud (the reference keeps R_/t_ and rewrites history rows 0..I-1; SVGDICP
   // rebuilds its optimizer in every stein_align, SVGDICP.cpp:73): restart the device-side iteration state, keep the poses.
   h->launches += launch_align_reset(h->ctrl.p, svgd ? h->opt_state.p : nullptr, svgd ? (size_t)12 * h->P_l : 0, st);
-  const SvgdArgs sv = svgd ? svgd_args(h) : SvgdArgs();
+  S.sv = svgd ? svgd_args(h) : SvgdArgs();
   if (svgd && h->optimizer < 0) {
     // SVGDICP.cpp:73-75: "No optimizer chosen" -> NO_OPTIMIZER before anything moves; the getters then describe the
     // untouched pose_particles_ (every rank holds all of it)
@@ -720,6 +737,7 @@ int svnicp_align(svnicp_handle h) {
     h->enqueued_iters = 0;
     h->ms_setup = h->ms_iter = h->ms_epi = h->ms_total = 0;
     h->aligned = true;
+    S.special = true;
     return SVNICP_NO_OPTIMIZER;
   }
 
@@ -753,7 +771,7 @@ int svnicp_align(svnicp_handle h) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev[1], st));
 
-  IterArgs ia;
+  IterArgs &ia = S.ia;
   memset(&ia, 0, sizeof(ia));
   ia.n_s = (int)h->n_s; ia.n_pad = h->n_pad; ia.K = h->K; ia.Kp = h->Kp; ia.cand_idx = h->prm.debug_corr ? h->cand_idx.p : nullptr;
   ia.P = h->P; ia.p_lo = h->p_lo; ia.P_l = h->P_l;
@@ -767,7 +785,7 @@ int svnicp_align(svnicp_handle h) {
   ia.dbg_idx = h->prm.debug_corr ? h->dbg_idx.p : nullptr;
   ia.dbg_mask = h->prm.debug_corr ? h->dbg_mask.p : nullptr;
 
-  SteinArgs sa;
+  SteinArgs &sa = S.sa;
   memset(&sa, 0, sizeof(sa));
   sa.P = h->P; sa.p_lo = h->p_lo; sa.P_l = h->P_l; sa.I = I;
   sa.svn_full_grad = h->prm.SVN_full_grad; sa.check_early_stop = h->prm.check_early_stop;
@@ -782,10 +800,9 @@ int svnicp_align(svnicp_handle h) {
   // SVN-ICP class: k_head (decide + median) on the side stream as soon as the poses of the iteration are final, overlapping
   // k_filter / k_gn; k_finalize and k_tail follow on the main stream.  Sharded without the peer exchange (NCCL fallback):
   // finalize -> ncclAllGather of the records -> k_head -> k_tail, all on the main stream.
-  const bool overlap = !svgd && (h->n_ranks == 1 || h->peer_mode);
-  PeerTable pt = h->pt;  // n_ranks == 1 view unless the peer exchange is up
-  const unsigned seq0 = h->seq;
-  cudaStream_t hs = h->head_stream;
+  const bool overlap = S.overlap = !svgd && (h->n_ranks == 1 || h->peer_mode);
+  S.pt = h->pt;  // n_ranks == 1 view unless the peer exchange is up
+  S.seq0 = h->seq;
 
   if (h->profile)
     while (h->prof_events.size() < (size_t)I * 7) {
@@ -799,14 +816,20 @@ int svnicp_align(svnicp_handle h) {
     h->launches += launch_prep(ia, st, 1, x_src);
     if (overlap) CU(cudaEventRecord(h->ev_x, st));
   }
-  // ---- iterations (SVNICP.cpp:52-108) ----
+  S.e = 0;
+  S.enqueue_done = I <= 0;
+  return SVNICP_OK;
+}
+
+// enqueue iteration S.e (SVNICP.cpp:52-108)
+static int align_step(svnicp_handle h, AlignState &S) {
+  ALIGN_LOCALS
   const int LAG = 3;
-  int e = 0;
-  for (; e < I; e++) {
+  const int e = S.e;
     if (h->prm.check_early_stop && e >= LAG) {
       // deterministic host cut: the stop flag as of the END of iteration e-LAG decides (identical on every rank)
       CU(cudaEventSynchronize(h->iter_events[e - LAG]));
-      if (h->h_stop[e - LAG]) break;
+      if (h->h_stop[e - LAG]) { S.enqueue_done = true; return SVNICP_OK; }
     }
 #define PROF(k) do { if (h->profile) CU(cudaEventRecord(h->prof_events[(size_t)e * 7 + (k)], st)); } while (0)
     PROF(0);
@@ -870,7 +893,14 @@ int svnicp_align(svnicp_handle h) {
       CU(cudaMemcpyAsync(&h->h_stop[e], &h->ctrl.p->stop, sizeof(int), cudaMemcpyDeviceToHost, st));
       CU(cudaEventRecord(h->iter_events[e], st));
     }
-  }
+    S.e = e + 1;
+  if (S.e >= I) S.enqueue_done = true;
+  return SVNICP_OK;
+}
+
+static int align_epilogue(svnicp_handle h, AlignState &S) {
+  ALIGN_LOCALS
+  const int e = S.e;
   h->enqueued_iters = e;
   h->seq = seq0 + (unsigned)e + 1u;
   CU(cudaEventRecord(h->ev[2], st));
@@ -898,6 +928,11 @@ int svnicp_align(svnicp_handle h) {
   CU(cudaMemcpyAsync(h->h_ctrl, h->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h->h_kept, h->kept_hist.p, ((size_t)I + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(h->ev[3], st));
+  return SVNICP_OK;
+}
+
+static int align_finish(svnicp_handle h, AlignState &S) {
+  ALIGN_LOCALS
   CU(cudaStreamSynchronize(st));
   h->iters_done = h->h_ctrl->iters_done;
   if (h->h_ctrl->error) return fail(h, SVNICP_ERR_CUDA, "peer exchange timed out: another rank did not publish its records (rank %d of %d)", h->rank, h->n_ranks);
@@ -921,6 +956,21 @@ int svnicp_align(svnicp_handle h) {
   h->fallback_queries = misc[1];
   h->aligned = true;
   return SVNICP_ALIGN_SUCCESS;
+}
+
+
+int svnicp_align(svnicp_handle h) {
+  if (!h) return SVNICP_ERR_INVALID;
+  AlignState S;
+  int rc = align_begin(h, S);
+  if (rc != SVNICP_OK) return rc;  // error, or SVNICP_NO_OPTIMIZER (SVGDICP.cpp:73-75)
+  while (!S.enqueue_done) {
+    rc = align_step(h, S);
+    if (rc != SVNICP_OK) return rc;
+  }
+  rc = align_epilogue(h, S);
+  if (rc != SVNICP_OK) return rc;
+  return align_finish(h, S);
 }
 
 #define NEED_ALIGNED(out)                                                              \
@@ -1171,6 +1221,78 @@ int svnicp_get_launch_count(svnicp_handle h, int64_t *out) {
   if (!h || !out) return SVNICP_ERR_INVALID;
   *out = h->launches;
   return SVNICP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Throughput mode (BASELINE.json configs[3]): several independent odometry streams on one GPU.  A batch owns one ordinary
+// handle per stream (own CUDA streams, own buffers); svnicp_batch_align enqueues the scans of all streams iteration by
+// iteration, round robin, so the short latency-bound kernels of one stream (pruning, finalize, Stein phase) run under
+// the Gauss-Newton pass of another.  Results are bit-identical to running each stream's handle on its own.
+// ---------------------------------------------------------------------------------------------------------------
+struct svnicp_batch_t {
+  std::vector<svnicp_handle> hs;
+  std::string err;
+};
+
+int svnicp_batch_create(svnicp_batch *out, const svnicp_params *params, int n_streams, int particle_count, const double *init_pose, int device) {
+  if (!out || !params || n_streams < 1 || n_streams > 4096) return fail(nullptr, SVNICP_ERR_INVALID, "svnicp_batch_create: bad argument");
+  *out = nullptr;
+  svnicp_batch b = new svnicp_batch_t();
+  for (int s = 0; s < n_streams; s++) {
+    svnicp_handle h = nullptr;
+    const int rc = svnicp_create(&h, params, particle_count, init_pose ? init_pose + (size_t)s * 6 * particle_count : nullptr, SVNICP_CLASS_SVNICP, device);
+    if (rc != SVNICP_OK) {
+      svnicp_batch_destroy(b);
+      return rc;  // message in svnicp_last_error(NULL)
+    }
+    b->hs.push_back(h);
+  }
+  *out = b;
+  return SVNICP_OK;
+}
+
+void svnicp_batch_destroy(svnicp_batch b) {
+  if (!b) return;
+  for (svnicp_handle h : b->hs) svnicp_destroy(h);
+  delete b;
+}
+
+const char *svnicp_batch_last_error(svnicp_batch b) { return b ? b->err.c_str() : g_create_error.c_str(); }
+
+int svnicp_batch_size(svnicp_batch b) { return b ? (int)b->hs.size() : SVNICP_ERR_INVALID; }
+
+svnicp_handle svnicp_batch_stream(svnicp_batch b, int s) { return (b && s >= 0 && s < (int)b->hs.size()) ? b->hs[(size_t)s] : nullptr; }
+
+int svnicp_batch_align(svnicp_batch b, int32_t *states) {
+  if (!b) return SVNICP_ERR_INVALID;
+  const size_t n = b->hs.size();
+  std::vector<AlignState> S(n);
+  std::vector<int> rc(n, SVNICP_OK);
+  auto note = [&](size_t s, int code) {
+    rc[s] = code;
+    if (code < 0) b->err = "stream " + std::to_string(s) + ": " + b->hs[s]->err;
+  };
+  for (size_t s = 0; s < n; s++) note(s, align_begin(b->hs[s], S[s]));
+  bool any = true;
+  while (any) {
+    any = false;
+    for (size_t s = 0; s < n; s++) {
+      if (rc[s] != SVNICP_OK || S[s].enqueue_done) continue;
+      note(s, align_step(b->hs[s], S[s]));
+      any = true;
+    }
+  }
+  for (size_t s = 0; s < n; s++)
+    if (rc[s] == SVNICP_OK) note(s, align_epilogue(b->hs[s], S[s]));
+  int worst = SVNICP_ALIGN_SUCCESS;
+  for (size_t s = 0; s < n; s++) {
+    if (rc[s] == SVNICP_OK) note(s, align_finish(b->hs[s], S[s]));
+    if (states) states[s] = rc[s];
+    if (rc[s] < 0) worst = rc[s];
+  }
+  for (size_t s = 0; s < n; s++)  // a stream that failed midway may still have work in flight
+    if (rc[s] < 0) { cudaSetDevice(b->hs[s]->device); cudaStreamSynchronize(b->hs[s]->stream); cudaStreamSynchronize(b->hs[s]->head_stream); }
+  return worst;
 }
 
 }  // extern "C"
