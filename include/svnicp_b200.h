@@ -81,6 +81,9 @@ typedef struct {
 #define SVNICP_FLAG_NO_PARTICLE_SORT 1  /* keep the caller's particle order internally (no pose-space ordering)      */
 #define SVNICP_FLAG_FILTER_FULL 2       /* prune from the full K-slot candidate table every iteration (no list reuse) */
 #define SVNICP_FLAG_NCCL_GATHER 8       /* sharded: ncclAllGather per iteration instead of the peer-memory exchange    */
+#define SVNICP_FLAG_DEBUG_SYNC 32       /* synchronise after every launch group of an iteration and log it to stderr      */
+#define SVNICP_FLAG_WATCHDOG 64         /* svnicp_align polls the streams instead of blocking and reports a scan that does not
+                                           finish within 8 s (which stream, the device-side iteration state) as an error     */
 #define SVNICP_FLAG_REUSE_STATS 16      /* svnicp_get_prune_stats reports the fraction of rows served by list reuse    */
 
 /* Fill with the defaults of SteinICPParam (SVGDICP.h:41-57). */

@@ -43,6 +43,8 @@ FLAG_NO_PARTICLE_SORT = 1
 FLAG_FILTER_FULL = 2
 FLAG_NCCL_GATHER = 8
 FLAG_REUSE_STATS = 16
+FLAG_DEBUG_SYNC = 32
+FLAG_WATCHDOG = 64
 
 
 @dataclasses.dataclass

@@ -10,6 +10,7 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -309,7 +310,7 @@ static int alloc_particle_state(svnicp_handle h) {
   CU(h->stats.ensure(48));
   CU(h->particles.ensure(6 * P));
   CU(h->xf.ensure(12 * P));
-  CU(h->hist.ensure((size_t)MED_PASSES * MED_BINS));
+  CU(h->hist.ensure((size_t)2 * MED_PASSES * MED_BINS, true));  // fast-path scratch + radix histograms (k_head_*)
   CU(h->prep_scratch_d.ensure((size_t)(h->P_l_max > h->sm_count ? h->P_l_max : h->sm_count) * 12 + 64, true));  // per-CTA centre partials of k_tail
   CU(h->prep_scratch_i.ensure(PRUNE_BINS + 8, true));
   CU(h->stamps.ensure(8, true));
@@ -831,13 +832,24 @@ static int align_step(svnicp_handle h, AlignState &S) {
       CU(cudaEventSynchronize(h->iter_events[e - LAG]));
       if (h->h_stop[e - LAG]) { S.enqueue_done = true; return SVNICP_OK; }
     }
-#define PROF(k) do { if (h->profile) CU(cudaEventRecord(h->prof_events[(size_t)e * 7 + (k)], st)); } while (0)
+// SVNICP_FLAG_DEBUG_SYNC: wait for the device after every launch group and say so on stderr (localises a hang or a fault)
+#define PROF(k)                                                                                          \
+  do {                                                                                                   \
+    if (h->profile) CU(cudaEventRecord(h->prof_events[(size_t)e * 7 + (k)], st));                        \
+    if (h->prm.flags & SVNICP_FLAG_DEBUG_SYNC) {                                                         \
+      fprintf(stderr, "[svnicp] iteration %d: before phase %d ...", e, (k));                             \
+      fflush(stderr);                                                                                    \
+      const cudaError_t e1__ = cudaStreamSynchronize(st), e2__ = cudaStreamSynchronize(hs);              \
+      fprintf(stderr, " main %s, head %s\n", cudaGetErrorString(e1__), cudaGetErrorString(e2__));        \
+      fflush(stderr);                                                                                    \
+    }                                                                                                    \
+  } while (0)
     PROF(0);
     if (svgd) h->launches += launch_prep(ia, st, 0, nullptr);
     else if (overlap) {
       CU(cudaStreamWaitEvent(hs, h->ev_x, 0));
       const int n = launch_head(sa, pt, (h->peer_mode && e > 0) ? seq0 + (unsigned)e : 0u, 0, hs);
-      if (n < 0) return fail(h, SVNICP_ERR_CUDA, "cooperative launch of k_head failed: %s", cudaGetErrorString(cudaGetLastError()));
+      if (n < 0) return fail(h, SVNICP_ERR_CUDA, "launch of k_head failed: %s", cudaGetErrorString(cudaGetLastError()));
       h->launches += n;
       CU(cudaEventRecord(h->ev_head, hs));
     }
@@ -879,7 +891,7 @@ static int align_step(svnicp_handle h, AlignState &S) {
         int rc = do_allgather(h, e & 1);  // NCCL fallback: whole records (x of this iteration + b, H, g)
         if (rc) return rc;
         const int n = launch_head(sa, pt, 0u, 0, st);
-        if (n < 0) return fail(h, SVNICP_ERR_CUDA, "cooperative launch of k_head failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (n < 0) return fail(h, SVNICP_ERR_CUDA, "launch of k_head failed: %s", cudaGetErrorString(cudaGetLastError()));
         h->launches += n;
       }
       PROF(5);
@@ -919,7 +931,7 @@ static int align_epilogue(svnicp_handle h, AlignState &S) {
         if (rc) return rc;
       }
     const int n = launch_head(sa, pt, (h->peer_mode && e > 0) ? seq0 + (unsigned)e : 0u, 1, st);
-    if (n < 0) return fail(h, SVNICP_ERR_CUDA, "cooperative launch of k_head failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (n < 0) return fail(h, SVNICP_ERR_CUDA, "launch of k_head failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += n + launch_stats(sa, 1, st);
   }
   CU(cudaGetLastError());
@@ -933,6 +945,26 @@ static int align_epilogue(svnicp_handle h, AlignState &S) {
 
 static int align_finish(svnicp_handle h, AlignState &S) {
   ALIGN_LOCALS
+  if (h->prm.flags & SVNICP_FLAG_WATCHDOG) {  // diagnostic watchdog: poll instead of blocking, report which stream is stuck and the device-side state
+    const double t0 = (double)clock() / CLOCKS_PER_SEC;
+    bool done = false;
+    while ((double)clock() / CLOCKS_PER_SEC - t0 < 8.0) {
+      if (cudaStreamQuery(st) == cudaSuccess && cudaStreamQuery(hs) == cudaSuccess) { done = true; break; }
+    }
+    if (!done) {
+      cudaStream_t aux;
+      cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking);
+      Ctrl c;
+      memset(&c, 0, sizeof(c));
+      cudaMemcpyAsync(&c, h->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, aux);
+      cudaStreamSynchronize(aux);
+      fprintf(stderr, "[svnicp watchdog] main %s, head %s; ctrl: stop %d iter %d iters_done %d error %d fin_ticket %u tail_ticket %u kept_total %llu bandwidth %g enqueued %d\n",
+              cudaGetErrorString(cudaStreamQuery(st)), cudaGetErrorString(cudaStreamQuery(hs)), c.stop, c.iter, c.iters_done, c.error, c.fin_ticket,
+              c.tail_ticket, c.kept_total, c.bandwidth, S.e);
+      fflush(stderr);
+      return fail(h, SVNICP_ERR_CUDA, "watchdog: scan did not finish");
+    }
+  }
   CU(cudaStreamSynchronize(st));
   h->iters_done = h->h_ctrl->iters_done;
   if (h->h_ctrl->error) return fail(h, SVNICP_ERR_CUDA, "peer exchange timed out: another rank did not publish its records (rank %d of %d)", h->rank, h->n_ranks);

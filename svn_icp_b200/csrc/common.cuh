@@ -55,6 +55,11 @@ struct Ctrl {
   unsigned long long sel_rank[MED_PASSES + 1];
   unsigned med_ticket[MED_PASSES];  // CTAs that finished pass s (the last one selects)
   unsigned long long kept_total;  // sum of ccount over rows (prune statistics)
+  // k_head_* (tail2.cu): fast median path around the previous iteration's median
+  unsigned fast_ticket[2];
+  int med_done;                   // 1: the bandwidth of this iteration is final (the radix passes return at once)
+  int pad3;
+  unsigned long long fast_bin, fast_rank;  // bin of the linear histogram that holds the median (0 / MED_BINS-1: miss) and the rank inside it
 };
 
 // ---- peer-memory exchange of the per-particle records between the GPUs of one box (sharded handles) -----------------

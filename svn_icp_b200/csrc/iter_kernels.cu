@@ -429,10 +429,10 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // FIRST: first-order mode of the SVGD-ICP class (SVGDICP::sgd_grad, SVGDICP.cpp:398-455): sum 0 counts the unmasked
 // pairs (nonzero_count, :404) and the second-moment sums 1..9 are not needed -- the gradient is E and C alone because
 // every Euler partial is [omega_k]x R (see svgd_class.cu).
-// Stage layout: [TB][Kp] float4 pruned lists, then [TB + 1] float4 row headers (source point R0 s, w = list length bits:
-// padded length << 16 | true length; 0 = padding row; slot TB is a dummy so the next row's header is prefetched unconditionally).
-constexpr int GN_SINGLE = (2 << 16) | 1;  // header bits of a row whose pruned list holds exactly one candidate
-
+// Stage layout: [TB][Kp] float4 pruned lists, then [TB] float4 row headers (source point R0 s, w = list length bits: padded
+// length << 16 | true length; 0 = padding row), then three 32-bit row masks written by the producer warp: rows whose padded list
+// length is 2, 4, and more.  The consumers walk the three classes one after the other with a loop body specialised for the
+// class (no data-dependent branch inside the two short-list bodies: control flow was 18 of 122 instructions per row).
 template <bool DBG, bool UNI, bool FIRST>
 __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a) {  // (.., 3) spills the fp64 accumulators: measured slower
   if (a.ctrl->stop) return;
@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
   const int n_tiles = a.n_pad / TB;
   const int slice = blockIdx.x, n_slices = gridDim.x;
   const int n_my = (slice < n_tiles) ? (n_tiles - slice + n_slices - 1) / n_slices : 0;
+  const size_t hdr_off = (size_t)TB * Kp * 16, msk_off = hdr_off + (size_t)TB * 16;
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) { mbar_init(full + s, 1); mbar_init(empty + s, GN_CONSUMERS / 32); }
@@ -453,22 +454,27 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
   __syncthreads();
 
   if (warp == GN_CONSUMERS / 32) {
-    // ---------------- producer warp: 1-D TMA bulk copies of the pruned lists ----------------
+    // ---------------- producer warp: 1-D TMA bulk copies of the pruned lists + the row-class masks ----------------
     for (int i = 0; i < n_my; i++) {
       const int s = i % S, k = i / S;
       mbar_wait(empty + s, (uint32_t)((k & 1) ^ 1));
       const int row0 = (slice + i * n_slices) * TB;
       unsigned char *st = smem + (size_t)s * stage_bytes;
       const int cnt = (lane < TB) ? (__float_as_int(a.hdr[row0 + lane].w) >> 16) : 0;
+      const unsigned m2 = __ballot_sync(0xffffffffu, cnt == 2), m4 = __ballot_sync(0xffffffffu, cnt == 4), ml = __ballot_sync(0xffffffffu, cnt > 4);
       int bytes = cnt * 16;
       int total = bytes;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
       total += TB * 16;
-      if (lane == 0) mbar_expect_tx(full + s, (uint32_t)total);
+      if (lane == 0) {
+        unsigned *msk = reinterpret_cast<unsigned *>(st + msk_off);
+        msk[0] = m2; msk[1] = m4; msk[2] = ml;
+        mbar_expect_tx(full + s, (uint32_t)total);  // arrive = release: the masks are visible to whoever sees the phase complete
+      }
       __syncwarp();
       if (lane < TB && cnt > 0) bulk_g2s(st + (size_t)lane * Kp * 16, a.clist + (size_t)(row0 + lane) * Kp, (uint32_t)bytes, full + s);
-      if (lane == 0) bulk_g2s(st + (size_t)TB * Kp * 16, a.hdr + row0, (uint32_t)(TB * 16), full + s);
+      if (lane == 0) bulk_g2s(st + hdr_off, a.hdr + row0, (uint32_t)(TB * 16), full + s);
     }
     return;
   }
@@ -492,117 +498,142 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
   int rows_in_acc = 0, flushes2 = 0;
   bool wrote = false;
   double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + (active ? l : 0)) * NACC;
-  const int row_step = RG * Kp;
+  // rows of a tile this thread owns: r = rg, rg + RG, ... (RG is a power of two dividing TB or larger than it)
+  unsigned rgmask = 0;
+  for (int r = rg; r < TB; r += RG) rgmask |= 1u << r;
 
-// squared distance to one candidate: fixed operation order (index parity with oracle_corr_f32)
-#define SVN_DIST(C, D)                                                                                 \
-  float D;                                                                                             \
-  {                                                                                                    \
-    const float dx_ = __fsub_rn(qx, (C).x), dy_ = __fsub_rn(qy, (C).y), dz_ = __fsub_rn(qz, (C).z);    \
-    D = __fmaf_rn(dz_, dz_, __fmaf_rn(dy_, dy_, __fmul_rn(dx_, dx_)));                                 \
-  }
-// ... and the running 1-NN: strict '<', first slot wins (mink.cuh:141)
-#define SVN_EVAL(C, SLOT)                                                                              \
-  {                                                                                                    \
-    SVN_DIST(C, d_)                                                                                    \
-    if (d_ < best) { best = d_; bi = (SLOT); }                                                         \
+// a = A' s' ; q = a + tau : query relative to q0_b.  Order fixed (index parity with oracle_corr_f32).
+#define SVN_QUERY                                                                                      \
+  const float ax = __fmaf_rn(A0, sv.x, __fmaf_rn(A1, sv.y, __fmul_rn(A2, sv.z)));                      \
+  const float ay = __fmaf_rn(A3, sv.x, __fmaf_rn(A4, sv.y, __fmul_rn(A5, sv.z)));                      \
+  const float az = __fmaf_rn(A6, sv.x, __fmaf_rn(A7, sv.y, __fmul_rn(A8, sv.z)));                      \
+  const float qx = __fadd_rn(ax, t0), qy = __fadd_rn(ay, t1), qz = __fadd_rn(az, t2);
+// residual and squared distance to one candidate: fixed operation order (index parity)
+#define SVN_DIST(C, T)                                                                                                       \
+  const float T##x = __fsub_rn(qx, (C).x), T##y = __fsub_rn(qy, (C).y), T##z = __fsub_rn(qz, (C).z);                          \
+  const float T##d = __fmaf_rn(T##z, T##z, __fmaf_rn(T##y, T##y, __fmul_rn(T##x, T##x)));
+// robust weight + the 16 Gauss-Newton sums for the matched pair (residual ex, ey, ez, squared distance best)
+#define SVN_ACCUM                                                                                                            \
+  {                                                                                                                          \
+    const bool valid = best < Dm; /* SVGDICP.cpp:332: squared distance vs un-squared max_dist (Q1) */                        \
+    if (DBG) {                                                                                                               \
+      if (active) {                                                                                                          \
+        /* recover the slot of the winner in the un-pruned table (first slot with identical coordinates) */                  \
+        const int row = (slice + i * n_slices) * TB + r;                                                                     \
+        const float4 *full_row = a.cand + (size_t)row * a.K;                                                                 \
+        const float wx_ = __fsub_rn(qx, ex) , wy_ = __fsub_rn(qy, ey), wz_ = __fsub_rn(qz, ez);                              \
+        int slot = 0;                                                                                                        \
+        float bd_ = INFINITY;                                                                                                \
+        for (int kk = 0; kk < a.K; kk++) { /* q - (q - c) is c up to one rounding: take the nearest table entry */            \
+          const float4 f = full_row[kk];                                                                                     \
+          const float dd_ = fabsf(f.x - wx_) + fabsf(f.y - wy_) + fabsf(f.z - wz_);                                          \
+          if (dd_ < bd_) { bd_ = dd_; slot = kk; }                                                                           \
+        }                                                                                                                    \
+        a.dbg_idx[(size_t)l * a.n_s + row] = a.cand_idx[(size_t)row * a.K + slot];                                           \
+        a.dbg_mask[(size_t)l * a.n_s + row] = valid ? 1 : 0;                                                                 \
+      }                                                                                                                      \
+    }                                                                                                                        \
+    /* rho = (D / (D + 3 |e|))^2  (SVNICP.cpp:120-122); masked pairs: rho' = 0 and +1 on the translation block (Q2) */       \
+    const float en = sqrt_approx(best);                                                                                      \
+    const float wq = Dm * rcp_approx(fmaf(3.0f, en, Dm));                                                                    \
+    const float rho = wq * wq;                                                                                               \
+    const float rp = valid ? rho : 0.0f;                                                                                     \
+    if (FIRST) {                                                                                                             \
+      acc[0] += valid ? 1.0f : 0.0f;                                                                                         \
+    } else {                                                                                                                 \
+      acc[0] += valid ? rho : 1.0f;                                                                                          \
+      const float gx = rp * sv.x, gy = rp * sv.y, gz = rp * sv.z;                                                            \
+      acc[1] += gx; acc[2] += gy; acc[3] += gz;                                                                              \
+      acc[4] = fmaf(gx, sv.x, acc[4]); acc[5] = fmaf(gx, sv.y, acc[5]); acc[6] = fmaf(gx, sv.z, acc[6]);                     \
+      acc[7] = fmaf(gy, sv.y, acc[7]); acc[8] = fmaf(gy, sv.z, acc[8]); acc[9] = fmaf(gz, sv.z, acc[9]);                     \
+    }                                                                                                                        \
+    const float fx = rp * ex, fy = rp * ey, fz = rp * ez; /* multiplication (not select): NaN must propagate */              \
+    acc[10] += fx; acc[11] += fy; acc[12] += fz;                                                                             \
+    const float wx = ax + sv.x, wy = ay + sv.y, wz = az + sv.z; /* R~ s in the world-oriented frame */                       \
+    acc[13] = fmaf(wy, fz, fmaf(-wz, fy, acc[13]));                                                                          \
+    acc[14] = fmaf(wz, fx, fmaf(-wx, fz, acc[14]));                                                                          \
+    acc[15] = fmaf(wx, fy, fmaf(-wy, fx, acc[15]));                                                                          \
   }
 
   for (int i = 0; i < n_my; i++) {
     const int s = i % S, k = i / S;
     mbar_wait(full + s, (uint32_t)(k & 1));
     const unsigned char *st = smem + (size_t)s * stage_bytes;
-    const float4 *hdr = reinterpret_cast<const float4 *>(st + (size_t)TB * Kp * 16);
+    const float4 *hdr = reinterpret_cast<const float4 *>(st + hdr_off);
+    const float4 *lists = reinterpret_cast<const float4 *>(st);
     if (UNI || active) {
-      const float4 *e = reinterpret_cast<const float4 *>(st) + (size_t)rg * Kp;
-      float4 sv = hdr[rg];
-      for (int r = rg; r < TB; r += RG, e += row_step) {
-        const float4 sv_nx = hdr[min(r + RG, TB)];  // software prefetch of the next row's header (slot TB: dummy)
-        const int bits = __float_as_int(sv.w);
-        if (bits != 0) {
-          float4 c0 = e[0], c1 = e[1], c2, c3;
-          const int n = bits >> 16;  // padded to 2, then a multiple of 4
-          if (n > 2) { c2 = e[2]; c3 = e[3]; }
-          // a = A' s' ; q = a + tau : query relative to q0_b.  Order fixed (index parity).
-          const float ax = __fmaf_rn(A0, sv.x, __fmaf_rn(A1, sv.y, __fmul_rn(A2, sv.z)));
-          const float ay = __fmaf_rn(A3, sv.x, __fmaf_rn(A4, sv.y, __fmul_rn(A5, sv.z)));
-          const float az = __fmaf_rn(A6, sv.x, __fmaf_rn(A7, sv.y, __fmul_rn(A8, sv.z)));
-          const float qx = __fadd_rn(ax, t0), qy = __fadd_rn(ay, t1), qz = __fadd_rn(az, t2);
-          // slot 0 always exists: its distance starts the search (same bits as an evaluation against best = +inf)
-          float ex = __fsub_rn(qx, c0.x), ey = __fsub_rn(qy, c0.y), ez = __fsub_rn(qz, c0.z);
-          float best = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
-          if (!(best == best)) best = INFINITY;  // NaN distance: later slots are compared against +inf, as MinK's strict '<' does
-          float4 cw = c0;
-          if (bits != GN_SINGLE) {  // warp-uniform: a one-candidate list needs no search at all
-            int bi = 0;
-            SVN_EVAL(c1, 1)
-            if (n > 2) { SVN_EVAL(c2, 2) SVN_EVAL(c3, 3) }
-            if (n > 4) {
-              // upper bound of |q| (distance of this particle's query from the initial-guess query q0_b)
-              const float qn = fmaf(sqrt_approx(fmaf(qz, qz, fmaf(qy, qy, qx * qx))), 1.00001f, 1e-7f);
-              int bk = 0;  // first slot of the chunk that holds the winner (0: one of the first four, bi is exact)
-              for (int k0 = 4; k0 < n; k0 += 4) {
-                c0 = e[k0]; c1 = e[k0 + 1]; c2 = e[k0 + 2]; c3 = e[k0 + 3];
-                // exact early exit: slots ascend in |c| (= c.w, a lower bound) and |q - c| >= |c| - |q|, so once
-                // (|c| - |q|)^2 > best no later slot can win or tie.  NaN anywhere compares false -> no exit.
-                const float tt = c0.w - qn;
-                const bool done = (tt > 0.f) && (tt * tt * 0.99999f > best);
-                if (UNI) { if (__all_sync(0xffffffffu, done)) break; }
-                else { if (done) break; }
-                // only the chunk minimum enters the running comparison (fminf drops NaN, like '<'); the slot inside the
-                // winning chunk is recovered afterwards: 7.5 instead of 9 instructions per candidate
-                SVN_DIST(c0, d0_) SVN_DIST(c1, d1_) SVN_DIST(c2, d2_) SVN_DIST(c3, d3_)
-                const float m_ = fminf(fminf(d0_, d1_), fminf(d2_, d3_));
-                if (m_ < best) { best = m_; bk = k0; }
-              }
-              if (bk != 0) {  // first slot of that chunk whose distance IS the minimum: what slot-by-slot strict '<' would have kept
-                c0 = e[bk]; c1 = e[bk + 1]; c2 = e[bk + 2];
-                SVN_DIST(c0, d0_) SVN_DIST(c1, d1_) SVN_DIST(c2, d2_)
-                bi = (d0_ == best) ? bk : (d1_ == best) ? bk + 1 : (d2_ == best) ? bk + 2 : bk + 3;
-              }
-            }
-            cw = e[bi];
-            ex = __fsub_rn(qx, cw.x); ey = __fsub_rn(qy, cw.y); ez = __fsub_rn(qz, cw.z);
-          }
-          const float wx_ = cw.x, wy_ = cw.y, wz_ = cw.z;  // DBG only: coordinates of the winner
-          const bool valid = best < Dm;  // SVGDICP.cpp:332: squared distance vs un-squared max_dist (Q1)
-          if (DBG) {
-            if (active) {
-              // recover the slot of the winner in the un-pruned table (first slot with identical coordinates)
-              const int row = (slice + i * n_slices) * TB + r;
-              const float4 *full_row = a.cand + (size_t)row * a.K;
-              int slot = 0;
-              for (int kk = 0; kk < a.K; kk++) {
-                const float4 f = full_row[kk];
-                if (f.x == wx_ && f.y == wy_ && f.z == wz_) { slot = kk; break; }
-              }
-              a.dbg_idx[(size_t)l * a.n_s + row] = a.cand_idx[(size_t)row * a.K + slot];
-              a.dbg_mask[(size_t)l * a.n_s + row] = valid ? 1 : 0;
-            }
-          }
-          // rho = (D / (D + 3 |e|))^2  (SVNICP.cpp:120-122); masked pairs: rho' = 0 and +1 on the translation block (Q2)
-          const float en = sqrt_approx(best);
-          const float wq = Dm * rcp_approx(fmaf(3.0f, en, Dm));
-          const float rho = wq * wq;
-          const float rp = valid ? rho : 0.0f;
-          if (FIRST) {
-            acc[0] += valid ? 1.0f : 0.0f;
-          } else {
-            acc[0] += valid ? rho : 1.0f;
-            const float gx = rp * sv.x, gy = rp * sv.y, gz = rp * sv.z;
-            acc[1] += gx; acc[2] += gy; acc[3] += gz;
-            acc[4] = fmaf(gx, sv.x, acc[4]); acc[5] = fmaf(gx, sv.y, acc[5]); acc[6] = fmaf(gx, sv.z, acc[6]);
-            acc[7] = fmaf(gy, sv.y, acc[7]); acc[8] = fmaf(gy, sv.z, acc[8]); acc[9] = fmaf(gz, sv.z, acc[9]);
-          }
-          const float fx = rp * ex, fy = rp * ey, fz = rp * ez;  // multiplication (not select): NaN must propagate
-          acc[10] += fx; acc[11] += fy; acc[12] += fz;
-          const float wx = ax + sv.x, wy = ay + sv.y, wz = az + sv.z;  // R~ s in the world-oriented frame
-          acc[13] = fmaf(wy, fz, fmaf(-wz, fy, acc[13]));
-          acc[14] = fmaf(wz, fx, fmaf(-wx, fz, acc[14]));
-          acc[15] = fmaf(wx, fy, fmaf(-wy, fx, acc[15]));
-          rows_in_acc++;
+      const unsigned *msk = reinterpret_cast<const unsigned *>(st + msk_off);
+      unsigned m2 = msk[0] & rgmask, m4 = msk[1] & rgmask, ml = msk[2] & rgmask;
+      rows_in_acc += __popc(m2 | m4 | ml);
+      // ---- lists of one or two candidates (padded to 2: a one-candidate list carries a +inf sentinel that never wins)
+      while (m2) {
+        const int r = __ffs(m2) - 1;
+        m2 &= m2 - 1;
+        const float4 sv = hdr[r];
+        const float4 *e = lists + r * Kp;
+        const float4 c0 = e[0], c1 = e[1];
+        SVN_QUERY
+        SVN_DIST(c0, u) SVN_DIST(c1, v)
+        const bool p1 = vd < ud;  // strict '<': the first slot wins ties (mink.cuh:141); NaN compares false -> slot 0
+        const float best = p1 ? vd : ud, ex = p1 ? vx : ux, ey = p1 ? vy : uy, ez = p1 ? vz : uz;
+        SVN_ACCUM
+      }
+      // ---- three or four candidates (padded to 4)
+      while (m4) {
+        const int r = __ffs(m4) - 1;
+        m4 &= m4 - 1;
+        const float4 sv = hdr[r];
+        const float4 *e = lists + r * Kp;
+        const float4 c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
+        SVN_QUERY
+        SVN_DIST(c0, u) SVN_DIST(c1, v) SVN_DIST(c2, w) SVN_DIST(c3, z)
+        // tournament with strict '<' at every node: among equal distances the lowest slot wins, as slot-by-slot '<' would decide
+        const bool p1 = vd < ud, p3 = zd < wd;
+        const float m01 = p1 ? vd : ud, m23 = p3 ? zd : wd;
+        const float e01x = p1 ? vx : ux, e01y = p1 ? vy : uy, e01z = p1 ? vz : uz;
+        const float e23x = p3 ? zx : wx, e23y = p3 ? zy : wy, e23z = p3 ? zz : wz;
+        const bool p = m23 < m01;
+        const float best = p ? m23 : m01, ex = p ? e23x : e01x, ey = p ? e23y : e01y, ez = p ? e23z : e01z;
+        SVN_ACCUM
+      }
+      // ---- longer lists: chunks of four, exact warp-voted early exit
+      while (ml) {
+        const int r = __ffs(ml) - 1;
+        ml &= ml - 1;
+        const float4 sv = hdr[r];
+        const float4 *e = lists + r * Kp;
+        const int n = __float_as_int(sv.w) >> 16;
+        float4 c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
+        SVN_QUERY
+        float best;
+        int bk = 0;  // first slot of the chunk that holds the running minimum
+        {
+          SVN_DIST(c0, u) SVN_DIST(c1, v) SVN_DIST(c2, w) SVN_DIST(c3, z)
+          best = fminf(fminf(ud, vd), fminf(wd, zd));  // fminf drops NaN, like a strict '<' against +inf
+          if (!(best == best)) best = INFINITY;
         }
-        sv = sv_nx;
+        // upper bound of |q| (distance of this particle's query from the initial-guess query q0_b)
+        const float qn = fmaf(sqrt_approx(fmaf(qz, qz, fmaf(qy, qy, qx * qx))), 1.00001f, 1e-7f);
+        for (int k0 = 4; k0 < n; k0 += 4) {
+          c0 = e[k0]; c1 = e[k0 + 1]; c2 = e[k0 + 2]; c3 = e[k0 + 3];
+          // exact early exit: slots ascend in |c| (= c.w, a lower bound) and |q - c| >= |c| - |q|, so once
+          // (|c| - |q|)^2 > best no later slot can win or tie.  NaN anywhere compares false -> no exit.
+          const float tt = c0.w - qn;
+          const bool done = (tt > 0.f) && (tt * tt * 0.99999f > best);
+          if (UNI) { if (__all_sync(0xffffffffu, done)) break; }
+          else { if (done) break; }
+          // only the chunk minimum enters the running comparison; the slot inside the winning chunk is recovered afterwards
+          SVN_DIST(c0, u) SVN_DIST(c1, v) SVN_DIST(c2, w) SVN_DIST(c3, z)
+          const float m_ = fminf(fminf(ud, vd), fminf(wd, zd));
+          if (m_ < best) { best = m_; bk = k0; }
+        }
+        // first slot of the winning chunk whose distance IS the minimum: what slot-by-slot strict '<' would have kept
+        c0 = e[bk]; c1 = e[bk + 1]; c2 = e[bk + 2]; c3 = e[bk + 3];
+        SVN_DIST(c0, u) SVN_DIST(c1, v) SVN_DIST(c2, w) SVN_DIST(c3, z)
+        const bool h0 = ud == best, h1 = vd == best, h2 = wd == best;
+        float ex = h0 ? ux : h1 ? vx : h2 ? wx : zx, ey = h0 ? uy : h1 ? vy : h2 ? wy : zy, ez = h0 ? uz : h1 ? vz : h2 ? wz : zz;
+        if (best == INFINITY) { ex = ux; ey = uy; ez = uz; }  // nothing compared below +inf (NaN query): slot 0, as before
+        SVN_ACCUM
       }
       if (rows_in_acc >= GN_FLUSH_ROWS) {
 #pragma unroll
@@ -621,7 +652,9 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);
   }
-#undef SVN_EVAL
+#undef SVN_QUERY
+#undef SVN_DIST
+#undef SVN_ACCUM
   if (active) {
 #pragma unroll
     for (int j = 0; j < NACC; j++) out[j] = (wrote ? out[j] : 0.0) + ((double)dacc[j] + (double)acc[j]);

@@ -106,8 +106,8 @@ int launch_filter(const IterArgs &a, cudaStream_t st);
 int launch_gn(const IterArgs &a, cudaStream_t st);
 int launch_finalize(const IterArgs &a, const PeerTable &pt, unsigned seq_h, cudaStream_t st);
 void init_iter_kernels();
-// bytes of one shared-memory stage of k_gn: TB pruned rows of K float4 + TB + 1 row headers (the last one a dummy), 128-byte aligned
-__host__ __device__ inline size_t gn_stage_bytes(int TB, int K) { return ((size_t)TB * K * 16 + (size_t)(TB + 1) * 16 + 127) & ~(size_t)127; }
+// bytes of one shared-memory stage of k_gn: TB pruned rows of K float4 + TB row headers + 3 row-class masks, 128-byte aligned
+__host__ __device__ inline size_t gn_stage_bytes(int TB, int K) { return ((size_t)TB * K * 16 + (size_t)TB * 16 + 16 + 127) & ~(size_t)127; }
 
 struct SteinArgs {
   int P, p_lo, P_l, I;
@@ -131,8 +131,8 @@ struct SteinArgs {
   double *stamps;                 // [8] globaltimer stamps of k_tail's phases (tuning aid; null = off)
   int sm_count;
 };
-// SVN-ICP class, Stein phase (tail2.cu): k_head = early-stop decision + history row + exact median bandwidth (cooperative,
-// small grid, off the critical path); k_tail = Stein step + pose update + next iteration's transforms and pruning ball.
+// SVN-ICP class, Stein phase (tail2.cu): k_head_* = early-stop decision + history row + exact median bandwidth (a chain of
+// small ordinary kernels, off the critical path); k_tail = Stein step + pose update + next iteration's transforms and pruning ball.
 // seq_x / seq_h / seq_x_out: sequence numbers of the peer exchange (0 = nothing to wait for).  Return launches or -1.
 int launch_head(const SteinArgs &a, const PeerTable &pt, unsigned seq_x, int epilogue, cudaStream_t st);
 int launch_tail(const SteinArgs &a, const IterArgs &ia, const PeerTable &pt, unsigned seq_h, unsigned seq_x_out, cudaStream_t st);

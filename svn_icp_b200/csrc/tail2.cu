@@ -1,6 +1,6 @@
 // tail2.cu -- the "Stein phase" of one SVN iteration as two kernels without a grid-wide barrier on the critical path.
 //
-//   k_head  (side stream, small cooperative grid; overlaps the correspondence + Gauss-Newton pass of the same iteration)
+//   k_head_* (side stream, a chain of small ordinary kernels; overlaps the correspondence + Gauss-Newton pass of the same iteration)
 //           early-stop decision for the previous update + its history row          SVNICP.cpp:95-107
 //           exact lower median of the P^2 pairwise squared distances -> bandwidth h   SVNICP.cpp:254-266
 //           Everything here depends only on the particle positions x, which are final as soon as the previous update is.
@@ -15,38 +15,62 @@
 // rank's record buffer over NVLink (PeerTable, common.cuh), followed by a sequence number in the peer's flag block; k_tail /
 // k_head spin on their local flags.  Records are double buffered by iteration parity, which is what makes the exchange
 // safe without a second handshake.  No NCCL call on the per-iteration path.
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace svn {
 
 // ---------------------------------------------------------------------------------------------
-// k_head
+// k_head_*: a chain of ordinary (non-cooperative) kernels on the side stream.  Each has a small footprint (128 threads,
+// <= 64 registers, 32 KB of shared memory) so that one CTA fits on every SM NEXT TO the two resident CTAs of k_gn and the
+// chain never pushes k_gn's persistent single-wave grid into a second wave; phases that need all CTAs to be done are
+// separated by kernel boundaries, and the CTA that finishes last (ticket) does the serial part.
+//   k_head_prep    peers' x arrived? -> early-stop decision for the previous update, its history row, SoA copy of x,
+//                  reset of the median scratch
+//   k_head_fast1/2 the median moves little between iterations: histogram LINEARLY around the previous one (8190 bins over
+//                  [0.5, 1.5) x previous median, one bin below, one above); then gather the few dozen values of the bin that
+//                  holds the rank and pick the exact order statistic.  Same value as the radix select (the lower median is
+//                  unique), so the bandwidth is bit-identical to the 5-pass path
+//   k_head_radix   x 5: exact radix select on the fp64 bit pattern (11 + 13 + 13 + 13 + 13 bits); returns at once when the fast
+//                  path already produced the median (first iteration of a scan, tiny particle sets and misses take this path)
+// (An earlier version was ONE cooperative kernel with grid-wide barriers; with the host blocked in cudaStreamSynchronize on the
+// main stream, the cooperative launch on the side stream did not start on small problems -- a hang that disappeared when the host
+// polled instead.  Plain launches have no such dependence.)
 // ---------------------------------------------------------------------------------------------
-constexpr int HD_THREADS = 512;
+constexpr int HD_THREADS = 128;
 constexpr int HD_WARPS = HD_THREADS / 32;
+constexpr int HD_COLLECT_CAP = 4096;  // doubles staged in the 32 KB histogram buffer
+static_assert(HD_COLLECT_CAP * sizeof(double) <= MED_BINS * sizeof(unsigned), "collected values are staged in the histogram buffer");
 
 __device__ __forceinline__ int hd_pass_bits(int s) { return s == 0 ? 11 : 13; }
 __device__ __forceinline__ int hd_bits_before(int s) { return s == 0 ? 0 : 11 + 13 * (s - 1); }
+__device__ __forceinline__ double hd_pair_d2(const double *__restrict__ X, int P, int i, int j) {
+  double s = 0.0;
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    const double df = X[d * P + i] - X[d * P + j];
+    s += df * df;  // SVNICP.cpp:257-260
+  }
+  return s;
+}
 
-// (prefix, rank) after a pass from its finished global histogram; every CTA computes the same values
+// (prefix, rank) after a pass from its finished global histogram (run by the last CTA of the pass)
 __device__ void hd_select(const unsigned *hist, unsigned long long prefix_in, unsigned long long rank_in, int nbins, int bits,
                           unsigned long long *prefix_out, unsigned long long *rank_out, unsigned long long *s_warp,
                           unsigned long long *s_res) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (nbins + nt - 1) / nt;  // <= 16 (8192 bins / 512 threads)
-  unsigned vals[16];
+  const int per = (nbins + nt - 1) / nt;  // contiguous run of bins per thread (64 for 8192 bins)
   unsigned long long loc = 0;
+  for (int i0 = 0; i0 < per; i0 += 16) {  // 16 loads in flight at a time
+    unsigned v[16];
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
-    const int b = tid * per + i;
-    vals[i] = (i < per && b < nbins) ? __ldcg(hist + b) : 0u;  // all loads in flight at once; kept in registers
-    loc += vals[i];
+    for (int u = 0; u < 16; u++) {
+      const int b = tid * per + i0 + u;
+      v[u] = (i0 + u < per && b < nbins) ? __ldcg(hist + b) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) loc += v[u];
   }
   unsigned long long incl = loc;
 #pragma unroll
@@ -60,16 +84,16 @@ __device__ void hd_select(const unsigned *hist, unsigned long long prefix_in, un
   unsigned long long wbase = 0;
   for (int w = 0; w < warp; w++) wbase += s_warp[w];
   const unsigned long long excl = wbase + incl - loc;
-  if (loc > 0 && excl <= rank_in && rank_in < excl + loc) {
+  if (loc > 0 && excl <= rank_in && rank_in < excl + loc) {  // exactly one thread owns the rank: it walks its (cache-hot) run again
     unsigned long long cum = excl;
-    int b = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      if (cum + vals[i] > rank_in) break;
-      cum += vals[i];
-      b = i + 1;
+    int b = tid * per;
+    for (int i = 0; i < per; i++) {
+      const unsigned v = (tid * per + i < nbins) ? __ldcg(hist + tid * per + i) : 0u;
+      if (cum + v > rank_in) break;
+      cum += v;
+      b = tid * per + i + 1;
     }
-    s_res[0] = (prefix_in << bits) | (unsigned long long)(tid * per + b);
+    s_res[0] = (prefix_in << bits) | (unsigned long long)b;
     s_res[1] = rank_in - cum;
   }
   __syncthreads();
@@ -78,16 +102,22 @@ __device__ void hd_select(const unsigned *hist, unsigned long long prefix_in, un
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(HD_THREADS, 1) k_head(SteinArgs a, PeerTable pt, unsigned seq_x, int epilogue, int xs_smem_bytes) {
-  cg::grid_group grid = cg::this_grid();
+// true in exactly one CTA: the one that finishes last.  All global writes of the other CTAs are visible to it.
+__device__ __forceinline__ bool hd_last_cta(unsigned *ticket, int *s_flag) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *s_flag = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!*s_flag) return false;
+  __threadfence();
+  return true;
+}
+
+__global__ void __launch_bounds__(HD_THREADS, 8) k_head_prep(SteinArgs a, PeerTable pt, unsigned seq_x, int epilogue) {
   Ctrl *c = a.ctrl;
   if (c->stop) return;  // set by an earlier launch: identical for every CTA
-  extern __shared__ __align__(16) unsigned char s_dyn[];  // optional copy of x [6][P] for the median passes
-  __shared__ __align__(16) unsigned s_hist[MED_BINS];     // 32 KB: histogram / collected candidates of the median bin
   __shared__ double s_red[HD_WARPS];
-  __shared__ unsigned long long s_warp[32], s_res[2];
-  __shared__ int s_flag[2];
-
+  __shared__ int s_stop;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gtid = blockIdx.x * blockDim.x + tid, gn = gridDim.x * blockDim.x;
   const int P = a.P;
@@ -95,184 +125,189 @@ __global__ void __launch_bounds__(HD_THREADS, 1) k_head(SteinArgs a, PeerTable p
   if (seq_x) peer_wait(pt, FLAG_X, seq_x, c);
   const int it = c->iter;
   const double *rec = a.rec + (size_t)(it & 1) * a.rec_stride;
-  // previous iteration's median (the bandwidth is rewritten only at the very end): the guess of the fast median path
-  const double med_guess = c->bandwidth * log((double)(P + 1));
-
-  // ------------------------------------------------------------------ decide (redundantly per CTA: same data, same order)
-  {
-    double s = 0.0;
-    for (int p = tid; p < P; p += blockDim.x) s += __ldcg(rec + (size_t)p * REC + REC_DNORM);
-    s = warp_sum(s);
-    if (lane == 0) s_red[warp] = s;
-    __syncthreads();
-    if (tid == 0) {
-      double tot = 0.0;
-      for (int w = 0; w < HD_WARPS; w++) tot += s_red[w];
-      const int stop = (a.check_early_stop && it > 0 && tot / (double)P < a.threshold) ? 1 : 0;  // SVNICP.cpp:95-101
-      s_flag[0] = stop;
-      if (blockIdx.x == 0) {
-        if (stop) { c->stop = 1; c->iters_done = it; }
-        else if (epilogue) c->iters_done = it;
-      }
+  // decide (redundantly per CTA: same data, same order)
+  double s = 0.0;
+  for (int p = tid; p < P; p += blockDim.x) s += __ldcg(rec + (size_t)p * REC + REC_DNORM);
+  s = warp_sum(s);
+  if (lane == 0) s_red[warp] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < HD_WARPS; w++) tot += s_red[w];
+    s_stop = (a.check_early_stop && it > 0 && tot / (double)P < a.threshold) ? 1 : 0;  // SVNICP.cpp:95-101
+  }
+  __syncthreads();
+  const bool stop = s_stop != 0;
+  if (!stop && it > 0 && it - 1 < a.I) {  // the history row of a stopping iteration is NOT written (Q9)
+    float *row = a.history + (size_t)(it - 1) * 6 * P;  // SVNICP.cpp:103-107
+    for (int i = gtid; i < 6 * P; i += gn) {
+      const int comp = i / P, p = i % P;
+      row[i] = (float)__ldcg(rec + (size_t)p * REC + REC_X + comp);
     }
-    __syncthreads();
-    if (s_flag[0]) return;  // break BEFORE the history row of that iteration (Q9); every CTA decides identically
-    if (it > 0 && it - 1 < a.I) {
-      float *row = a.history + (size_t)(it - 1) * 6 * P;  // SVNICP.cpp:103-107
-      for (int i = gtid; i < 6 * P; i += gn) {
-        const int comp = i / P, p = i % P;
-        row[i] = (float)__ldcg(rec + (size_t)p * REC + REC_X + comp);
-      }
-    }
-    if (epilogue || P < 2) return;
+  }
+  if (!stop && !epilogue && P >= 2) {
     for (int i = gtid; i < 6 * P; i += gn) {
       const int comp = i / P, p = i % P;
       a.xs[i] = __ldcg(rec + (size_t)p * REC + REC_X + comp);
     }
-    for (int i = gtid; i < MED_PASSES * MED_BINS; i += gn) a.hist[i] = 0u;
+    for (int i = gtid; i < 2 * MED_PASSES * MED_BINS; i += gn) a.hist[i] = 0u;  // fast-path scratch + radix histograms
   }
-  grid.sync();
+  if (gtid == 0) {
+    // Ctrl is written last and by one thread: every CTA of this launch has read `stop` at its top (possibly still 0), and the
+    // decision above does not depend on it
+    if (stop) { c->stop = 1; c->iters_done = it; }
+    else if (epilogue) c->iters_done = it;
+    c->med_done = 0;
+    c->fast_bin = 0ull;
+    c->fast_rank = 0ull;
+    c->fast_ticket[0] = c->fast_ticket[1] = 0u;
+    for (int q = 0; q < MED_PASSES; q++) c->med_ticket[q] = 0u;
+    c->sel_prefix[0] = 0ull;
+    c->sel_rank[0] = ((unsigned long long)P * (unsigned long long)P - 1ull) / 2ull;  // lower median
+  }
+}
 
-  // ------------------------------------------------------------------ bandwidth: exact lower median
+__global__ void __launch_bounds__(HD_THREADS, 8) k_head_fast1(SteinArgs a) {
+  Ctrl *c = a.ctrl;
+  const int P = a.P, it = c->iter;
+  if (c->stop || P < 8 || it == 0) return;
+  const double med_guess = c->bandwidth * log((double)(P + 1));  // previous iteration's median
+  if (!(med_guess > 0.0 && med_guess < INFINITY)) return;
+  __shared__ __align__(16) unsigned s_hist[MED_BINS];
+  __shared__ unsigned long long s_warp[32], s_res[2];
+  __shared__ int s_flag;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const double lo = 0.5 * med_guess, hi = 1.5 * med_guess, scale = (double)(MED_BINS - 2) / (hi - lo);
+  for (int i = tid; i < MED_BINS; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
   const double *X = a.xs;
-  if (xs_smem_bytes > 0) {
-    double *sx = reinterpret_cast<double *>(s_dyn);
-    for (int i = tid; i < 6 * P; i += blockDim.x) sx[i] = __ldcg(a.xs + i);
-    __syncthreads();
-    X = sx;
-  }
-  unsigned long long prefix = 0ull, rank = ((unsigned long long)P * (unsigned long long)P - 1ull) / 2ull;
-  bool have_median = false;
-  double median = 0.0;
-  // ---- fast path (2 passes instead of 5): the median moves little between iterations, so histogram LINEARLY around the
-  // previous one (8190 bins over [0.5, 1.5) x previous median, one bin below, one above), then gather the few dozen
-  // values of the bin that holds the rank and pick the exact order statistic.  Same value as the radix select (the
-  // lower median is unique), so the bandwidth is bit-identical to the 5-pass path; any miss (median left the window,
-  // degenerate bin) falls back to it.  Every branch below depends only on data all CTAs see identically.
-  constexpr int COLLECT_CAP = 4096;  // doubles; staged in s_hist (32 KB)
-  if (P >= 64 && it > 0 && med_guess > 0.0 && med_guess < INFINITY) {
-    const double lo = 0.5 * med_guess, hi = 1.5 * med_guess, scale = (double)(MED_BINS - 2) / (hi - lo);
-    auto bin_of = [&](double d) -> unsigned {  // monotone non-decreasing in d; NaN sorts last like its bit pattern
-      if (d < lo) return 0u;
-      if (!(d < hi)) return (unsigned)(MED_BINS - 1);
-      const int b = (int)((d - lo) * scale);
-      return 1u + (unsigned)min(b, MED_BINS - 3);
-    };
-    for (int i = tid; i < MED_BINS; i += blockDim.x) s_hist[i] = 0u;
-    __syncthreads();
-    for (int i = blockIdx.x; i < P; i += gridDim.x)
-      for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
-        const int j = j0 + tid;
-        unsigned bin = 0;
-        if (j < P) {
-          double d2 = 0.0;
-#pragma unroll
-          for (int d = 0; d < 6; d++) {
-            const double df = X[d * P + i] - X[d * P + j];
-            d2 += df * df;
-          }
-          bin = bin_of(d2);
-        }
-        const unsigned mm = __ballot_sync(0xffffffffu, j < P);
-        if (j < P) {
-          const unsigned peers = __match_any_sync(mm, bin);
-          if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));
-        }
+  for (int i = blockIdx.x; i < P; i += gridDim.x)
+    for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
+      const int j = j0 + tid;
+      unsigned bin = 0;
+      if (j < P) {
+        const double d2 = hd_pair_d2(X, P, i, j);
+        // monotone non-decreasing in d; NaN sorts last like its bit pattern
+        if (d2 < lo) bin = 0u;
+        else if (!(d2 < hi)) bin = (unsigned)(MED_BINS - 1);
+        else bin = 1u + (unsigned)min((int)((d2 - lo) * scale), MED_BINS - 3);
       }
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&s_hist[0], (unsigned)P);  // the diagonal: exact zeros, below lo
-    __syncthreads();
-    for (int i = tid; i < MED_BINS; i += blockDim.x)
-      if (s_hist[i]) atomicAdd(&a.hist[i], s_hist[i]);
-    grid.sync();
-    unsigned long long tbin = 0ull, trank = 0ull;
-    hd_select(a.hist, 0ull, rank, MED_BINS, 13, &tbin, &trank, s_warp, s_res);
-    if (tbin != 0ull && tbin != (unsigned long long)(MED_BINS - 1)) {
-      // gather the values of that bin once per unordered pair (each stands for two entries of the P x P matrix)
-      unsigned *cursor = a.hist + MED_BINS;                                   // zeroed with the histograms
-      double *list = reinterpret_cast<double *>(a.hist + 2 * MED_BINS);       // rows 2..4: 12288 doubles
-      for (int i = blockIdx.x; i < P; i += gridDim.x)
-        for (int j = i + 1 + tid; j < P; j += blockDim.x) {
-          double d2 = 0.0;
-#pragma unroll
-          for (int d = 0; d < 6; d++) {
-            const double df = X[d * P + i] - X[d * P + j];
-            d2 += df * df;
-          }
-          if (bin_of(d2) == (unsigned)tbin) {
-            const unsigned k = atomicAdd(cursor, 1u);
-            if (k < (unsigned)COLLECT_CAP) list[k] = d2;
-          }
-        }
-      grid.sync();
-      const unsigned n_c = __ldcg(cursor);
-      if (n_c >= 1u && n_c <= (unsigned)COLLECT_CAP) {
-        double *sl = reinterpret_cast<double *>(s_hist);
-        for (unsigned k = tid; k < n_c; k += blockDim.x) sl[k] = __ldcg(list + k);
-        if (tid == 0) s_flag[1] = 0;
-        __syncthreads();
-        const unsigned target = (unsigned)(trank >> 1);  // index among the distinct pairs of the bin, ascending
-        for (unsigned k = tid; k < n_c; k += blockDim.x) {
-          const double v = sl[k];
-          unsigned less = 0, eq = 0;
-          for (unsigned u = 0; u < n_c; u++) {
-            const double w = sl[u];
-            less += (w < v) ? 1u : 0u;
-            eq += (w == v) ? 1u : 0u;
-          }
-          if (less <= target && target < less + eq) { s_res[0] = (unsigned long long)__double_as_longlong(v); s_flag[1] = 1; }
-        }
-        __syncthreads();
-        if (s_flag[1]) { have_median = true; median = __longlong_as_double((long long)s_res[0]); }
-        __syncthreads();
+      const unsigned mm = __ballot_sync(0xffffffffu, j < P);
+      if (j < P) {
+        const unsigned peers = __match_any_sync(mm, bin);
+        if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));  // D_ij = D_ji
       }
     }
-    if (!have_median) {  // miss: clean the scratch the radix passes expect to be zero
-      for (int i = gtid; i < MED_PASSES * MED_BINS; i += gn) a.hist[i] = 0u;
-      grid.sync();
-    }
-  }
-  for (int s = 0; s < MED_PASSES && !have_median; s++) {
-    const int nb = 1 << hd_pass_bits(s);
-    for (int i = tid; i < nb; i += blockDim.x) s_hist[i] = 0u;
-    __syncthreads();
-    const int consumed = hd_bits_before(s);
-    const int shift = 63 - consumed - hd_pass_bits(s);
-    const unsigned bmask = (unsigned)(nb - 1);
-    // upper triangle, each D_ij = D_ji counted twice; lanes that fall into the same bin are aggregated with
-    // match.any before the shared-memory atomic (the first pass puts nearly every pair into 2-3 exponent bins)
-    for (int i = blockIdx.x; i < P; i += gridDim.x)
-      for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
-        const int j = j0 + tid;
-        bool match = false;
-        unsigned bin = 0;
-        if (j < P) {
-          double d2 = 0.0;
-#pragma unroll
-          for (int d = 0; d < 6; d++) {
-            const double df = X[d * P + i] - X[d * P + j];
-            d2 += df * df;  // SVNICP.cpp:257-260
-          }
-          const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
-          match = (consumed == 0) || ((key >> (63 - consumed)) == prefix);
-          bin = (unsigned)(key >> shift) & bmask;
-        }
-        const unsigned mm = __ballot_sync(0xffffffffu, match);
-        if (match) {
-          const unsigned peers = __match_any_sync(mm, bin);
-          if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));
-        }
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&s_hist[0], (unsigned)P);  // the diagonal: exact zeros, below lo
+  __syncthreads();
+  for (int i = tid; i < MED_BINS; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&a.hist[i], s_hist[i]);
+  if (!hd_last_cta(&c->fast_ticket[0], &s_flag)) return;
+  unsigned long long tbin = 0ull, trank = 0ull;
+  hd_select(a.hist, 0ull, ((unsigned long long)P * (unsigned long long)P - 1ull) / 2ull, MED_BINS, 13, &tbin, &trank, s_warp, s_res);
+  if (tid == 0) { c->fast_bin = tbin; c->fast_rank = trank; }
+}
+
+__global__ void __launch_bounds__(HD_THREADS, 8) k_head_fast2(SteinArgs a) {
+  Ctrl *c = a.ctrl;
+  const int P = a.P;
+  if (c->stop || P < 8) return;
+  const unsigned long long tbin = c->fast_bin;
+  if (tbin == 0ull || tbin == (unsigned long long)(MED_BINS - 1)) return;  // no fast path this iteration, or the median left the window
+  __shared__ __align__(16) double s_list[HD_COLLECT_CAP];
+  __shared__ int s_flag, s_found;
+  __shared__ unsigned long long s_val;
+  const int tid = threadIdx.x;
+  const double med_guess = c->bandwidth * log((double)(P + 1));
+  const double lo = 0.5 * med_guess, hi = 1.5 * med_guess, scale = (double)(MED_BINS - 2) / (hi - lo);
+  unsigned *cursor = a.hist + MED_BINS;                              // zeroed by k_head_prep
+  double *list = reinterpret_cast<double *>(a.hist + 2 * MED_BINS);  // rows 2..4: 12288 doubles
+  const double *X = a.xs;
+  // gather the values of that bin once per unordered pair (each stands for two entries of the P x P matrix)
+  for (int i = blockIdx.x; i < P; i += gridDim.x)
+    for (int j = i + 1 + tid; j < P; j += blockDim.x) {
+      const double d2 = hd_pair_d2(X, P, i, j);
+      if (d2 < lo || !(d2 < hi)) continue;
+      const unsigned bin = 1u + (unsigned)min((int)((d2 - lo) * scale), MED_BINS - 3);
+      if (bin == (unsigned)tbin) {
+        const unsigned k = atomicAdd(cursor, 1u);
+        if (k < (unsigned)HD_COLLECT_CAP) list[k] = d2;
       }
-    // the P diagonal entries are exact zeros (key 0): they match only an all-zero prefix and fall into bin 0
-    if (blockIdx.x == 0 && tid == 0 && (consumed == 0 || prefix == 0ull)) atomicAdd(&s_hist[0], (unsigned)P);
-    __syncthreads();
-    unsigned *gh = a.hist + (size_t)s * MED_BINS;
-    for (int i = tid; i < nb; i += blockDim.x)
-      if (s_hist[i]) atomicAdd(&gh[i], s_hist[i]);
-    grid.sync();
-    hd_select(gh, prefix, rank, nb, hd_pass_bits(s), &prefix, &rank, s_warp, s_res);
+    }
+  if (!hd_last_cta(&c->fast_ticket[1], &s_flag)) return;
+  const unsigned n_c = __ldcg(cursor);
+  if (n_c < 1u || n_c > (unsigned)HD_COLLECT_CAP) return;  // degenerate bin: the radix passes take over
+  for (unsigned k = tid; k < n_c; k += blockDim.x) s_list[k] = __ldcg(list + k);
+  if (tid == 0) s_found = 0;
+  __syncthreads();
+  const unsigned target = (unsigned)(c->fast_rank >> 1);  // index among the distinct pairs of the bin, ascending
+  for (unsigned k = tid; k < n_c; k += blockDim.x) {
+    const double v = s_list[k];
+    unsigned less = 0, eq = 0;
+    for (unsigned u = 0; u < n_c; u++) {
+      const double w = s_list[u];
+      less += (w < v) ? 1u : 0u;
+      eq += (w == v) ? 1u : 0u;
+    }
+    if (less <= target && target < less + eq) { s_val = (unsigned long long)__double_as_longlong(v); s_found = 1; }
   }
-  if (!have_median) median = __longlong_as_double((long long)prefix);
-  if (gtid == 0) c->bandwidth = median / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
+  __syncthreads();
+  if (tid == 0 && s_found) {
+    c->bandwidth = __longlong_as_double((long long)s_val) / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
+    c->med_done = 1;
+  }
+}
+
+// one radix-select pass over the upper triangle of D (D_ij = D_ji counted twice, diagonal once); the last CTA turns the
+// histogram into the next (prefix, rank) and, after the final pass, into the bandwidth
+__global__ void __launch_bounds__(HD_THREADS, 8) k_head_radix(SteinArgs a, int s) {
+  Ctrl *c = a.ctrl;
+  const int P = a.P;
+  if (c->stop || c->med_done || P < 2) return;
+  __shared__ __align__(16) unsigned s_hist[MED_BINS];
+  __shared__ unsigned long long s_warp[32], s_res[2];
+  __shared__ int s_flag;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned long long prefix = c->sel_prefix[s];
+  const int nb = 1 << hd_pass_bits(s);
+  for (int i = tid; i < nb; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
+  const int consumed = hd_bits_before(s);
+  const int shift = 63 - consumed - hd_pass_bits(s);
+  const unsigned bmask = (unsigned)(nb - 1);
+  const double *X = a.xs;
+  // lanes that fall into the same bin are aggregated with match.any before the shared-memory atomic (the first pass puts
+  // nearly every pair into 2-3 exponent bins)
+  for (int i = blockIdx.x; i < P; i += gridDim.x)
+    for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
+      const int j = j0 + tid;
+      bool match = false;
+      unsigned bin = 0;
+      if (j < P) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(hd_pair_d2(X, P, i, j));
+        match = (consumed == 0) || ((key >> (63 - consumed)) == prefix);
+        bin = (unsigned)(key >> shift) & bmask;
+      }
+      const unsigned mm = __ballot_sync(0xffffffffu, match);
+      if (match) {
+        const unsigned peers = __match_any_sync(mm, bin);
+        if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));
+      }
+    }
+  // the P diagonal entries are exact zeros (key 0): they match only an all-zero prefix and fall into bin 0
+  if (blockIdx.x == 0 && tid == 0 && (consumed == 0 || prefix == 0ull)) atomicAdd(&s_hist[0], (unsigned)P);
+  __syncthreads();
+  unsigned *gh = a.hist + (size_t)(MED_PASSES + s) * MED_BINS;  // the radix histograms sit behind the fast-path scratch
+  for (int i = tid; i < nb; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&gh[i], s_hist[i]);
+  if (!hd_last_cta(&c->med_ticket[s], &s_flag)) return;
+  unsigned long long np, nr;
+  hd_select(gh, prefix, c->sel_rank[s], nb, hd_pass_bits(s), &np, &nr, s_warp, s_res);
+  if (tid == 0) {
+    c->sel_prefix[s + 1] = np;
+    c->sel_rank[s + 1] = nr;
+    if (s == MED_PASSES - 1) c->bandwidth = __longlong_as_double((long long)np) / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -660,26 +695,30 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
 // launchers
 // ---------------------------------------------------------------------------------------------
 int head_grid(int P, int sm_count) {
-  // the median sweeps P^2/2 pairs: a few fat CTAs while that is small (cheap grid barrier, leaves the SMs to k_gn), all SMs for large P
+  // the median sweeps P^2/2 pairs: ~4096 per CTA and pass; at most one CTA per SM
   long long pairs = (long long)P * P / 2;
-  long long g = (pairs + 32767) / 32768;
-  if (g < 8) g = 8;
+  long long g = (pairs + 4095) / 4096;
+  if (g < 4) g = 4;
   if (g > sm_count) g = sm_count;
   if (P < 2) g = 1;
   return (int)g;
 }
 
 int launch_head(const SteinArgs &a, const PeerTable &pt, unsigned seq_x, int epilogue, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024); attr = true; }
-  int grid = epilogue ? 4 : head_grid(a.P, a.sm_count);
-  int xs_bytes = 6 * a.P * (int)sizeof(double);
-  if (xs_bytes > 144 * 1024 || a.P < 2 || epilogue) xs_bytes = 0;  // large P: read x through L2 instead
-  SteinArgs aa = a;
-  PeerTable pp = pt;
-  void *args[] = {(void *)&aa, (void *)&pp, (void *)&seq_x, (void *)&epilogue, (void *)&xs_bytes};
-  const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_head, dim3(grid), dim3(HD_THREADS), args, (size_t)xs_bytes, st);
-  return e == cudaSuccess ? 1 : -1;
+  int gp = (6 * a.P + HD_THREADS * 4 - 1) / (HD_THREADS * 4);
+  if (gp < 1) gp = 1;
+  if (gp > 32) gp = 32;
+  k_head_prep<<<epilogue ? 4 : gp, HD_THREADS, 0, st>>>(a, pt, seq_x, epilogue);
+  if (epilogue || a.P < 2) return 1;
+  const int g = head_grid(a.P, a.sm_count);
+  int n = 1;
+  if (a.P >= 8) {
+    k_head_fast1<<<g, HD_THREADS, 0, st>>>(a);
+    k_head_fast2<<<g, HD_THREADS, 0, st>>>(a);
+    n += 2;
+  }
+  for (int s = 0; s < MED_PASSES; s++) k_head_radix<<<g, HD_THREADS, 0, st>>>(a, s);
+  return n + MED_PASSES;
 }
 
 void tail_shape(int P_l, int sm_count, int *NI, int *JQ, int *stages, size_t *smem) {

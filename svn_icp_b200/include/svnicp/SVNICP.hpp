@@ -80,7 +80,7 @@ class SVGDICP {  // the base interface the node holds (OdometryPipeline.h:125)
   explicit SVGDICP(const SteinICPParam &parameters, const std::vector<double> &init_pose, int device = -1)
       : SVGDICP(parameters, init_pose, ParticleWeightOpt{}, SVNICP_CLASS_SVGDICP, device) {}
   virtual ~SVGDICP() {
-    if (h_) svnicp_destroy(h_);
+    if (h_ && owned_) svnicp_destroy(h_);
   }
   SVGDICP(const SVGDICP &) = delete;
   SVGDICP &operator=(const SVGDICP &) = delete;
@@ -168,14 +168,73 @@ class SVGDICP {  // the base interface the node holds (OdometryPipeline.h:125)
   void check(int rc, const char *what) const {
     if (rc < 0) throw Error(std::string(what) + ": " + svnicp_last_error(h_));
   }
+  /** a view of a handle owned by someone else (SVNICPBatch) */
+  SVGDICP(svnicp_handle borrowed, int particle_size) : h_(borrowed), particle_size_(particle_size), owned_(false) {}
   svnicp_handle h_ = nullptr;
   int particle_size_ = 0;
+  bool owned_ = true;
+  friend class SVNICPBatch;
 };
 
 class SVNICP final : public SVGDICP {  // SVNICP.h:29-80
  public:
   explicit SVNICP(const SteinICPParam &param, const std::vector<double> &init_pose, const ParticleWeightOpt &opt = {}, int device = -1)
       : SVGDICP(param, init_pose, opt, SVNICP_CLASS_SVNICP, device) {}
+
+ private:
+  SVNICP(svnicp_handle borrowed, int particle_size) : SVGDICP(borrowed, particle_size) {}
+  friend class SVNICPBatch;
+};
+
+/** The hand-off after the getters in ICP mode: updater_ (OdometryPipeline.cpp:37-45) with tensor2gtsamPose3 (ICPUtils.cpp:84-98):
+ *  pose = initial_guess * Pose3(Rot3::Expmap(mean[3:6]), mean[0:3]), mean = get_transformation(). */
+inline InitialMean compose_pose(const InitialMean &initial_guess, const std::vector<double> &mean6) {
+  InitialMean out;
+  if (mean6.size() != 6 || svnicp_pose_compose(initial_guess.R.data(), initial_guess.t.data(), mean6.data(), out.R.data(), out.t.data()) != SVNICP_OK)
+    throw Error("compose_pose: mean must hold 6 doubles");
+  return out;
+}
+
+/** Throughput mode (BASELINE.json configs[3]; no reference counterpart): S independent SVN-ICP streams on one GPU.  stream(s)
+ *  is an ordinary SVNICP bound to stream s (add_cloud / set_initial_mean / getters); stein_align() runs the scans of all streams
+ *  interleaved so that they overlap on the GPU.  Every stream's result is bit-identical to SVNICP::stein_align on its own. */
+class SVNICPBatch {
+ public:
+  /** init_poses: [S][6][P] */
+  SVNICPBatch(const SteinICPParam &p, int n_streams, int particle_size, const std::vector<double> &init_poses, int device = -1) {
+    if ((int64_t)init_poses.size() != (int64_t)n_streams * 6 * particle_size) throw Error("SVNICPBatch: init_poses must hold S*6*P doubles");
+    svnicp_params c;
+    svnicp_default_params(&c);
+    c.iterations = p.iterations;
+    c.lr = p.lr;
+    c.max_dist = p.max_dist;
+    c.check_early_stop = p.check_early_stop;
+    c.convergence_threshold = p.convergence_threshold;
+    c.KNN_count = p.KNN_count;
+    c.SVN_full_grad = p.SVN_full_grad;
+    if (svnicp_batch_create(&b_, &c, n_streams, particle_size, init_poses.data(), device) != SVNICP_OK)
+      throw Error(std::string("svnicp_batch_create: ") + svnicp_last_error(nullptr));
+    for (int s = 0; s < n_streams; s++) streams_.emplace_back(new SVNICP(svnicp_batch_stream(b_, s), particle_size));
+  }
+  ~SVNICPBatch() {
+    streams_.clear();
+    if (b_) svnicp_batch_destroy(b_);
+  }
+  SVNICPBatch(const SVNICPBatch &) = delete;
+  SVNICPBatch &operator=(const SVNICPBatch &) = delete;
+  int size() const { return (int)streams_.size(); }
+  SVNICP &stream(int s) { return *streams_.at((size_t)s); }
+  std::vector<SteinICPState> stein_align() {
+    std::vector<int32_t> st(streams_.size());
+    if (svnicp_batch_align(b_, st.data()) < 0) throw Error(std::string("batch stein_align: ") + svnicp_batch_last_error(b_));
+    std::vector<SteinICPState> out;
+    for (int32_t v : st) out.push_back(static_cast<SteinICPState>(v));
+    return out;
+  }
+
+ private:
+  svnicp_batch b_ = nullptr;
+  std::vector<std::unique_ptr<SVNICP>> streams_;
 };
 
 }  // namespace svnicp

@@ -31,6 +31,20 @@ class ScanPreprocessor {
   /** the reference's running maximum of the SQUARED point norm (OdometryPipeline.cpp:699), updated by crop_pointcloud */
   double scan_max_range_ = 0;
 
+  /** deskew_pointcloud (OdometryPipeline.cpp:357-447): stamps = the message's per-point time field widened to double (host
+   *  array of n; nullptr with kitti = true, the `/kitti/velo/pointcloud` branch :385-399); start / finish = the two newest
+   *  poses of the node's pose buffer (:419-422), rotation row-major + translation.  moved (optional) = false when all stamps
+   *  are equal and the cloud is returned unchanged (:415). */
+  DeviceCloudF32 deskew_pointcloud(const float *xyz, int64_t n, const double *stamps, const double R_start[9], const double t_start[3],
+                                   const double R_finish[9], const double t_finish[3], bool kitti = false, bool on_device = false,
+                                   bool *moved = nullptr) {
+    DeviceCloudF32 out;
+    int32_t mv = 0;
+    check(svnicp_pre_deskew(p_, xyz, n, on_device, stamps, 0, kitti, R_start, t_start, R_finish, t_finish, &out.xyz, &mv), "deskew_pointcloud");
+    out.n = n;
+    if (moved) *moved = mv != 0;
+    return out;
+  }
   /** crop_pointcloud (OdometryPipeline.cpp:692-704) */
   DeviceCloudF32 crop_pointcloud(const float *xyz, int64_t n, double min_range, double max_range, bool on_device = false) {
     DeviceCloudF32 out;

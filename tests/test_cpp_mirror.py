@@ -33,6 +33,39 @@ def test_mirror_compiles_and_links(tmp_path):
     assert subprocess.call([os.path.join(tmp_path, "abi")]) == 0
 
 
+def test_mirror_batch_and_handoff_compile_and_run(tmp_path):
+    """SVNICPBatch / compose_pose / ScanPreprocessor::deskew_pointcloud of the C++ mirror compile against the C ABI; compose_pose
+    is host arithmetic and runs here, the batch constructor must fail loudly without a GPU (no CPU fallback)."""
+    from svn_icp_b200 import build
+    lib = build.build()
+    src = os.path.join(tmp_path, "check.cpp")
+    open(src, "w").write("""
+#include "svnicp/SVNICP.hpp"
+#include "svnicp/ScanPreprocessor.hpp"
+#include "svnicp/VoxelHashMap.hpp"
+int main() {
+  svnicp::InitialMean g;
+  auto q = svnicp::compose_pose(g, std::vector<double>{0.1, 0.2, 0.3, 0.01, 0.02, 0.03});
+  if (q.t[0] != 0.1 || q.t[2] != 0.3) return 1;
+  int devs = 0;
+  svnicp::SteinICPParam p;
+  std::vector<double> ip(2 * 6 * 4, 0.0);
+  try {
+    svnicp::SVNICPBatch b(p, 2, 4, ip);
+    if (b.size() != 2) return 2;
+    devs = 1;
+  } catch (const svnicp::Error &) {
+  }
+  return devs ? 10 : 0;
+}
+""")
+    exe = os.path.join(tmp_path, "check")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "svn_icp_b200", "include"), src, "-o", exe, lib,
+                           "-Wl,-rpath," + os.path.dirname(lib)])
+    import torch
+    assert subprocess.call([exe]) == (10 if torch.cuda.is_available() else 0)
+
+
 def test_stein_msgs_producer_mapping(tmp_path):
     """stein_msgs field mapping (svnicp/stein_msgs_compat.hpp): [6][P] slices -> x,y,z,roll,pitch,yaw, as
     OdometryPipeline.cpp:942-987 does.  Pure host code: runs without a GPU."""
