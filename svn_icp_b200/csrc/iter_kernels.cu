@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
     // ---------------- producer warp: 1-D TMA bulk copies of the pruned lists + the row-class masks ----------------
     for (int i = 0; i < n_my; i++) {
       const int s = i % S, k = i / S;
-      mbar_wait(empty + s, (uint32_t)((k & 1) ^ 1));
+      mbar_wait_backoff(empty + s, (uint32_t)((k & 1) ^ 1));
       const int row0 = (slice + i * n_slices) * TB;
       unsigned char *st = smem + (size_t)s * stage_bytes;
       const int cnt = (lane < TB) ? (__float_as_int(a.hdr[row0 + lane].w) >> 16) : 0;
@@ -512,12 +512,13 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
 #define SVN_DIST(C, T)                                                                                                       \
   const float T##x = __fsub_rn(qx, (C).x), T##y = __fsub_rn(qy, (C).y), T##z = __fsub_rn(qz, (C).z);                          \
   const float T##d = __fmaf_rn(T##z, T##z, __fmaf_rn(T##y, T##y, __fmul_rn(T##x, T##x)));
-// robust weight + the 16 Gauss-Newton sums for the matched pair (residual ex, ey, ez, squared distance best)
-#define SVN_ACCUM                                                                                                            \
+// robust weight + the 16 Gauss-Newton sums for the matched pair (residual ex, ey, ez, squared distance best).
+// LIVE = false turns the row into a no-op (the phantom second row of an odd-sized pair, see the two-candidate class).
+#define SVN_ACCUM(LIVE)                                                                                                      \
   {                                                                                                                          \
     const bool valid = best < Dm; /* SVGDICP.cpp:332: squared distance vs un-squared max_dist (Q1) */                        \
     if (DBG) {                                                                                                               \
-      if (active) {                                                                                                          \
+      if (active && (LIVE)) {                                                                                                        \
         /* recover the slot of the winner in the un-pruned table (first slot with identical coordinates) */                  \
         const int row = (slice + i * n_slices) * TB + r;                                                                     \
         const float4 *full_row = a.cand + (size_t)row * a.K;                                                                 \
@@ -537,11 +538,11 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
     const float en = sqrt_approx(best);                                                                                      \
     const float wq = Dm * rcp_approx(fmaf(3.0f, en, Dm));                                                                    \
     const float rho = wq * wq;                                                                                               \
-    const float rp = valid ? rho : 0.0f;                                                                                     \
+    const float rp = (valid && (LIVE)) ? rho : 0.0f;                                                                         \
     if (FIRST) {                                                                                                             \
-      acc[0] += valid ? 1.0f : 0.0f;                                                                                         \
+      acc[0] += (valid && (LIVE)) ? 1.0f : 0.0f;                                                                             \
     } else {                                                                                                                 \
-      acc[0] += valid ? rho : 1.0f;                                                                                          \
+      acc[0] += (LIVE) ? (valid ? rho : 1.0f) : 0.0f;                                                                                        \
       const float gx = rp * sv.x, gy = rp * sv.y, gz = rp * sv.z;                                                            \
       acc[1] += gx; acc[2] += gy; acc[3] += gz;                                                                              \
       acc[4] = fmaf(gx, sv.x, acc[4]); acc[5] = fmaf(gx, sv.y, acc[5]); acc[6] = fmaf(gx, sv.z, acc[6]);                     \
@@ -565,18 +566,39 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
       const unsigned *msk = reinterpret_cast<const unsigned *>(st + msk_off);
       unsigned m2 = msk[0] & rgmask, m4 = msk[1] & rgmask, ml = msk[2] & rgmask;
       rows_in_acc += __popc(m2 | m4 | ml);
-      // ---- lists of one or two candidates (padded to 2: a one-candidate list carries a +inf sentinel that never wins)
+      // ---- lists of one or two candidates (padded to 2: a one-candidate list carries a +inf sentinel that never wins).
+      // Two rows per trip, written as one straight-line block so that the scheduler interleaves the two independent
+      // chains (4.5 warps per SM sub-partition do not hide the LDS / MUFU / FMA latencies of a single chain: 39 % of the
+      // issue slots went to `wait` and `short scoreboard` stalls); an odd last row is paired with a dead copy of itself.
       while (m2) {
-        const int r = __ffs(m2) - 1;
+        const int r0 = __ffs(m2) - 1;
         m2 &= m2 - 1;
-        const float4 sv = hdr[r];
-        const float4 *e = lists + r * Kp;
-        const float4 c0 = e[0], c1 = e[1];
-        SVN_QUERY
-        SVN_DIST(c0, u) SVN_DIST(c1, v)
-        const bool p1 = vd < ud;  // strict '<': the first slot wins ties (mink.cuh:141); NaN compares false -> slot 0
-        const float best = p1 ? vd : ud, ex = p1 ? vx : ux, ey = p1 ? vy : uy, ez = p1 ? vz : uz;
-        SVN_ACCUM
+        const bool two = m2 != 0;
+        const int r1 = two ? __ffs(m2) - 1 : r0;
+        m2 &= m2 - 1;
+        const float4 sv0 = hdr[r0], sv1 = hdr[r1];
+        const float4 *e0 = lists + r0 * Kp, *e1 = lists + r1 * Kp;
+        const float4 c00 = e0[0], c01 = e0[1], c10 = e1[0], c11 = e1[1];
+        {
+          const int r = r0;
+          (void)r;
+          const float4 sv = sv0;
+          SVN_QUERY
+          SVN_DIST(c00, u) SVN_DIST(c01, v)
+          const bool p1 = vd < ud;  // strict '<': the first slot wins ties (mink.cuh:141); NaN compares false -> slot 0
+          const float best = p1 ? vd : ud, ex = p1 ? vx : ux, ey = p1 ? vy : uy, ez = p1 ? vz : uz;
+          SVN_ACCUM(true)
+        }
+        {
+          const int r = r1;
+          (void)r;
+          const float4 sv = sv1;
+          SVN_QUERY
+          SVN_DIST(c10, u) SVN_DIST(c11, v)
+          const bool p1 = vd < ud;
+          const float best = p1 ? vd : ud, ex = p1 ? vx : ux, ey = p1 ? vy : uy, ez = p1 ? vz : uz;
+          SVN_ACCUM(two)
+        }
       }
       // ---- three or four candidates (padded to 4)
       while (m4) {
@@ -594,7 +616,7 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
         const float e23x = p3 ? zx : wx, e23y = p3 ? zy : wy, e23z = p3 ? zz : wz;
         const bool p = m23 < m01;
         const float best = p ? m23 : m01, ex = p ? e23x : e01x, ey = p ? e23y : e01y, ez = p ? e23z : e01z;
-        SVN_ACCUM
+        SVN_ACCUM(true)
       }
       // ---- longer lists: chunks of four, exact warp-voted early exit
       while (ml) {
@@ -633,7 +655,7 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
         const bool h0 = ud == best, h1 = vd == best, h2 = wd == best;
         float ex = h0 ? ux : h1 ? vx : h2 ? wx : zx, ey = h0 ? uy : h1 ? vy : h2 ? wy : zy, ez = h0 ? uz : h1 ? vz : h2 ? wz : zz;
         if (best == INFINITY) { ex = ux; ey = uy; ez = uz; }  // nothing compared below +inf (NaN query): slot 0, as before
-        SVN_ACCUM
+        SVN_ACCUM(true)
       }
       if (rows_in_acc >= GN_FLUSH_ROWS) {
 #pragma unroll
@@ -704,8 +726,10 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a, PeerTable pt, unsi
 #pragma unroll
     for (int i = 0; i < 36; i++) H[i] = 0.0;
     const double trS2 = S2[0] + S2[4] + S2[8];
+#pragma unroll
     for (int i = 0; i < 3; i++) {
       H[7 * i] = W + 1e-6;  // SVNICP.cpp:153 (Q3); translation block = sum(rho') + #masked (Q2)
+#pragma unroll
       for (int j = 0; j < 3; j++) H[6 * (3 + i) + 3 + j] = ((i == j) ? trS2 : 0.0) - S2[3 * i + j];
       H[7 * (3 + i)] += 1e-6;
     }
@@ -713,7 +737,9 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a, PeerTable pt, unsi
     H[0 * 6 + 4] = S1[2];  H[0 * 6 + 5] = -S1[1];
     H[1 * 6 + 3] = -S1[2]; H[1 * 6 + 5] = S1[0];
     H[2 * 6 + 3] = S1[1];  H[2 * 6 + 4] = -S1[0];
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
       for (int j = 0; j < 3; j++) H[6 * (3 + i) + j] = H[6 * j + 3 + i];
     double b[6];
     // b_t = R~^T E, b_r = R~^T C
@@ -724,7 +750,9 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a, PeerTable pt, unsi
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) s_out[REC_B + i] = b[i];
+#pragma unroll
     for (int r = 0; r < 6; r++)
+#pragma unroll
       for (int c = r; c < 6; c++) s_out[REC_H + tri(r, c)] = H[6 * r + c];
     double g[6];
 #pragma unroll
@@ -732,7 +760,7 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a, PeerTable pt, unsi
     if (!a.svn_full_grad) {  // g = H^-1 b, SVNICP.cpp:162 (only consumed by the pre-conditioned SVGD step)
 #pragma unroll
       for (int i = 0; i < 6; i++) g[i] = b[i];
-      lu_solve6(H, g, 1);
+      lu_solve6_reg(H, g);  // register resident (the record fields were taken from H above)
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) s_out[REC_G + i] = g[i];
@@ -763,7 +791,14 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a, PeerTable pt, unsi
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 void init_iter_kernels() {
-#define SVN_GN_ATTR(D, U, F) cudaFuncSetAttribute(k_gn<D, U, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+// dynamic shared memory up to 200 KB, and the SM configured for the maximum shared-memory carve-out while k_gn runs: its two
+// CTAs take ~156 KB, and the small side-stream kernels (k_head_*, 33 KB each) must find room NEXT to them instead of waiting for
+// a k_gn CTA to retire (with the default carve-out the head chain finished ~26 us after k_gn, on the critical path)
+#define SVN_GN_ATTR(D, U, F)                                                                                  \
+  do {                                                                                                        \
+    cudaFuncSetAttribute(k_gn<D, U, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);             \
+    cudaFuncSetAttribute(k_gn<D, U, F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+  } while (0)
   SVN_GN_ATTR(false, true, false); SVN_GN_ATTR(true, true, false); SVN_GN_ATTR(false, false, false); SVN_GN_ATTR(true, false, false);
   SVN_GN_ATTR(false, true, true); SVN_GN_ATTR(true, true, true); SVN_GN_ATTR(false, false, true); SVN_GN_ATTR(true, false, true);
 #undef SVN_GN_ATTR

@@ -167,6 +167,87 @@ __global__ void __launch_bounds__(HD_THREADS, 8) k_head_prep(SteinArgs a, PeerTa
   }
 }
 
+// ---- the pair sweeps, shared by the multi-CTA chain and the single-CTA kernel (cta / n_cta: this CTA's share of the rows) ----
+struct HdWindow {  // linear histogram window of the fast path: [0.5, 1.5) x the previous median
+  double lo, hi, scale;
+  __device__ __forceinline__ unsigned bin(double d2) const {  // monotone non-decreasing in d; NaN sorts last like its bit pattern
+    if (d2 < lo) return 0u;
+    if (!(d2 < hi)) return (unsigned)(MED_BINS - 1);
+    return 1u + (unsigned)min((int)((d2 - lo) * scale), MED_BINS - 3);
+  }
+};
+__device__ __forceinline__ HdWindow hd_window(double med_guess) {
+  HdWindow w;
+  w.lo = 0.5 * med_guess; w.hi = 1.5 * med_guess; w.scale = (double)(MED_BINS - 2) / (w.hi - w.lo);
+  return w;
+}
+// lanes that fall into the same bin are aggregated with match.any before the shared-memory atomic
+__device__ __forceinline__ void hd_hist_add(unsigned *s_hist, bool on, unsigned bin, int lane) {
+  const unsigned mm = __ballot_sync(0xffffffffu, on);
+  if (on) {
+    const unsigned peers = __match_any_sync(mm, bin);
+    if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));  // D_ij = D_ji: counted twice
+  }
+}
+__device__ void hd_fast_hist(const double *X, int P, const HdWindow &w, unsigned *s_hist, int cta, int n_cta) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = cta; i < P; i += n_cta)
+    for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
+      const int j = j0 + tid;
+      hd_hist_add(s_hist, j < P, j < P ? w.bin(hd_pair_d2(X, P, i, j)) : 0u, lane);
+    }
+  if (cta == 0 && tid == 0) atomicAdd(&s_hist[0], (unsigned)P);  // the diagonal: exact zeros, below lo
+}
+// values of bin tbin, once per unordered pair (each stands for two entries of the P x P matrix)
+__device__ void hd_fast_gather(const double *X, int P, const HdWindow &w, unsigned tbin, double *list, unsigned *cursor, int cta, int n_cta) {
+  for (int i = cta; i < P; i += n_cta)
+    for (int j = i + 1 + threadIdx.x; j < P; j += blockDim.x) {
+      const double d2 = hd_pair_d2(X, P, i, j);
+      if (w.bin(d2) == tbin) {
+        const unsigned k = atomicAdd(cursor, 1u);
+        if (k < (unsigned)HD_COLLECT_CAP) list[k] = d2;
+      }
+    }
+}
+// exact order statistic `target` (ascending, among the n_c collected values) -> *out; returns false if none found (cannot happen)
+__device__ bool hd_pick(const double *s_list, unsigned n_c, unsigned target, unsigned long long *s_val, int *s_found, double *out) {
+  if (threadIdx.x == 0) *s_found = 0;
+  __syncthreads();
+  for (unsigned k = threadIdx.x; k < n_c; k += blockDim.x) {
+    const double v = s_list[k];
+    unsigned less = 0, eq = 0;
+    for (unsigned u = 0; u < n_c; u++) {
+      const double x = s_list[u];
+      less += (x < v) ? 1u : 0u;
+      eq += (x == v) ? 1u : 0u;
+    }
+    if (less <= target && target < less + eq) { *s_val = (unsigned long long)__double_as_longlong(v); *s_found = 1; }
+  }
+  __syncthreads();
+  if (*s_found) *out = __longlong_as_double((long long)*s_val);
+  return *s_found != 0;
+}
+// one radix pass: upper triangle, D_ij = D_ji counted twice, diagonal once (exact zeros: key 0)
+__device__ void hd_radix_hist(const double *X, int P, int s, unsigned long long prefix, unsigned *s_hist, int cta, int n_cta) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int consumed = hd_bits_before(s), nb = 1 << hd_pass_bits(s);
+  const int shift = 63 - consumed - hd_pass_bits(s);
+  const unsigned bmask = (unsigned)(nb - 1);
+  for (int i = cta; i < P; i += n_cta)
+    for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
+      const int j = j0 + tid;
+      bool match = false;
+      unsigned bin = 0;
+      if (j < P) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(hd_pair_d2(X, P, i, j));
+        match = (consumed == 0) || ((key >> (63 - consumed)) == prefix);
+        bin = (unsigned)(key >> shift) & bmask;
+      }
+      hd_hist_add(s_hist, match, bin, lane);
+    }
+  if (cta == 0 && tid == 0 && (consumed == 0 || prefix == 0ull)) atomicAdd(&s_hist[0], (unsigned)P);
+}
+
 __global__ void __launch_bounds__(HD_THREADS, 8) k_head_fast1(SteinArgs a) {
   Ctrl *c = a.ctrl;
   const int P = a.P, it = c->iter;
@@ -176,29 +257,10 @@ __global__ void __launch_bounds__(HD_THREADS, 8) k_head_fast1(SteinArgs a) {
   __shared__ __align__(16) unsigned s_hist[MED_BINS];
   __shared__ unsigned long long s_warp[32], s_res[2];
   __shared__ int s_flag;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const double lo = 0.5 * med_guess, hi = 1.5 * med_guess, scale = (double)(MED_BINS - 2) / (hi - lo);
+  const int tid = threadIdx.x;
   for (int i = tid; i < MED_BINS; i += blockDim.x) s_hist[i] = 0u;
   __syncthreads();
-  const double *X = a.xs;
-  for (int i = blockIdx.x; i < P; i += gridDim.x)
-    for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
-      const int j = j0 + tid;
-      unsigned bin = 0;
-      if (j < P) {
-        const double d2 = hd_pair_d2(X, P, i, j);
-        // monotone non-decreasing in d; NaN sorts last like its bit pattern
-        if (d2 < lo) bin = 0u;
-        else if (!(d2 < hi)) bin = (unsigned)(MED_BINS - 1);
-        else bin = 1u + (unsigned)min((int)((d2 - lo) * scale), MED_BINS - 3);
-      }
-      const unsigned mm = __ballot_sync(0xffffffffu, j < P);
-      if (j < P) {
-        const unsigned peers = __match_any_sync(mm, bin);
-        if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));  // D_ij = D_ji
-      }
-    }
-  if (blockIdx.x == 0 && tid == 0) atomicAdd(&s_hist[0], (unsigned)P);  // the diagonal: exact zeros, below lo
+  hd_fast_hist(a.xs, P, hd_window(med_guess), s_hist, blockIdx.x, gridDim.x);
   __syncthreads();
   for (int i = tid; i < MED_BINS; i += blockDim.x)
     if (s_hist[i]) atomicAdd(&a.hist[i], s_hist[i]);
@@ -218,48 +280,22 @@ __global__ void __launch_bounds__(HD_THREADS, 8) k_head_fast2(SteinArgs a) {
   __shared__ int s_flag, s_found;
   __shared__ unsigned long long s_val;
   const int tid = threadIdx.x;
-  const double med_guess = c->bandwidth * log((double)(P + 1));
-  const double lo = 0.5 * med_guess, hi = 1.5 * med_guess, scale = (double)(MED_BINS - 2) / (hi - lo);
   unsigned *cursor = a.hist + MED_BINS;                              // zeroed by k_head_prep
   double *list = reinterpret_cast<double *>(a.hist + 2 * MED_BINS);  // rows 2..4: 12288 doubles
-  const double *X = a.xs;
-  // gather the values of that bin once per unordered pair (each stands for two entries of the P x P matrix)
-  for (int i = blockIdx.x; i < P; i += gridDim.x)
-    for (int j = i + 1 + tid; j < P; j += blockDim.x) {
-      const double d2 = hd_pair_d2(X, P, i, j);
-      if (d2 < lo || !(d2 < hi)) continue;
-      const unsigned bin = 1u + (unsigned)min((int)((d2 - lo) * scale), MED_BINS - 3);
-      if (bin == (unsigned)tbin) {
-        const unsigned k = atomicAdd(cursor, 1u);
-        if (k < (unsigned)HD_COLLECT_CAP) list[k] = d2;
-      }
-    }
+  hd_fast_gather(a.xs, P, hd_window(c->bandwidth * log((double)(P + 1))), (unsigned)tbin, list, cursor, blockIdx.x, gridDim.x);
   if (!hd_last_cta(&c->fast_ticket[1], &s_flag)) return;
   const unsigned n_c = __ldcg(cursor);
   if (n_c < 1u || n_c > (unsigned)HD_COLLECT_CAP) return;  // degenerate bin: the radix passes take over
   for (unsigned k = tid; k < n_c; k += blockDim.x) s_list[k] = __ldcg(list + k);
-  if (tid == 0) s_found = 0;
-  __syncthreads();
-  const unsigned target = (unsigned)(c->fast_rank >> 1);  // index among the distinct pairs of the bin, ascending
-  for (unsigned k = tid; k < n_c; k += blockDim.x) {
-    const double v = s_list[k];
-    unsigned less = 0, eq = 0;
-    for (unsigned u = 0; u < n_c; u++) {
-      const double w = s_list[u];
-      less += (w < v) ? 1u : 0u;
-      eq += (w == v) ? 1u : 0u;
-    }
-    if (less <= target && target < less + eq) { s_val = (unsigned long long)__double_as_longlong(v); s_found = 1; }
-  }
-  __syncthreads();
-  if (tid == 0 && s_found) {
-    c->bandwidth = __longlong_as_double((long long)s_val) / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
+  double median = 0.0;
+  // index among the distinct pairs of the bin, ascending: every value stands for two entries of the matrix
+  if (hd_pick(s_list, n_c, (unsigned)(c->fast_rank >> 1), &s_val, &s_found, &median) && tid == 0) {
+    c->bandwidth = median / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
     c->med_done = 1;
   }
 }
 
-// one radix-select pass over the upper triangle of D (D_ij = D_ji counted twice, diagonal once); the last CTA turns the
-// histogram into the next (prefix, rank) and, after the final pass, into the bandwidth
+// one radix-select pass; the last CTA turns the histogram into the next (prefix, rank) and, after the final pass, into the bandwidth
 __global__ void __launch_bounds__(HD_THREADS, 8) k_head_radix(SteinArgs a, int s) {
   Ctrl *c = a.ctrl;
   const int P = a.P;
@@ -267,35 +303,12 @@ __global__ void __launch_bounds__(HD_THREADS, 8) k_head_radix(SteinArgs a, int s
   __shared__ __align__(16) unsigned s_hist[MED_BINS];
   __shared__ unsigned long long s_warp[32], s_res[2];
   __shared__ int s_flag;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const unsigned long long prefix = c->sel_prefix[s];
   const int nb = 1 << hd_pass_bits(s);
   for (int i = tid; i < nb; i += blockDim.x) s_hist[i] = 0u;
   __syncthreads();
-  const int consumed = hd_bits_before(s);
-  const int shift = 63 - consumed - hd_pass_bits(s);
-  const unsigned bmask = (unsigned)(nb - 1);
-  const double *X = a.xs;
-  // lanes that fall into the same bin are aggregated with match.any before the shared-memory atomic (the first pass puts
-  // nearly every pair into 2-3 exponent bins)
-  for (int i = blockIdx.x; i < P; i += gridDim.x)
-    for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
-      const int j = j0 + tid;
-      bool match = false;
-      unsigned bin = 0;
-      if (j < P) {
-        const unsigned long long key = (unsigned long long)__double_as_longlong(hd_pair_d2(X, P, i, j));
-        match = (consumed == 0) || ((key >> (63 - consumed)) == prefix);
-        bin = (unsigned)(key >> shift) & bmask;
-      }
-      const unsigned mm = __ballot_sync(0xffffffffu, match);
-      if (match) {
-        const unsigned peers = __match_any_sync(mm, bin);
-        if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));
-      }
-    }
-  // the P diagonal entries are exact zeros (key 0): they match only an all-zero prefix and fall into bin 0
-  if (blockIdx.x == 0 && tid == 0 && (consumed == 0 || prefix == 0ull)) atomicAdd(&s_hist[0], (unsigned)P);
+  hd_radix_hist(a.xs, P, s, prefix, s_hist, blockIdx.x, gridDim.x);
   __syncthreads();
   unsigned *gh = a.hist + (size_t)(MED_PASSES + s) * MED_BINS;  // the radix histograms sit behind the fast-path scratch
   for (int i = tid; i < nb; i += blockDim.x)
@@ -308,6 +321,89 @@ __global__ void __launch_bounds__(HD_THREADS, 8) k_head_radix(SteinArgs a, int s
     c->sel_rank[s + 1] = nr;
     if (s == MED_PASSES - 1) c->bandwidth = __longlong_as_double((long long)np) / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
   }
+}
+
+// Small particle sets (P <= HD_SMALL_P): the whole chain in ONE CTA -- one launch instead of eight, no inter-CTA hand-over.
+// Same steps, same helpers, same values.  x is staged in shared memory; the histogram of a pass goes through the global
+// scratch only because hd_select reads it from there.
+constexpr int HD_SMALL_P = 64;  // one CTA of 128 threads: 2016 pairs, ~15 us; beyond that the chain over many CTAs is faster (measured at 100 and 256)
+__global__ void __launch_bounds__(HD_THREADS, 8) k_head_small(SteinArgs a, PeerTable pt, unsigned seq_x, int epilogue) {
+  Ctrl *c = a.ctrl;
+  if (c->stop) return;
+  __shared__ __align__(16) unsigned s_hist[MED_BINS];      // histogram / collected values (32 KB)
+  __shared__ __align__(16) double s_x[6 * HD_SMALL_P];     // 12 KB
+  __shared__ double s_red[HD_WARPS];
+  __shared__ unsigned long long s_warp[32], s_res[2], s_val;
+  __shared__ unsigned s_cursor;
+  __shared__ int s_stop, s_found;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = a.P;
+  if (seq_x) peer_wait(pt, FLAG_X, seq_x, c);
+  const int it = c->iter;
+  const double *rec = a.rec + (size_t)(it & 1) * a.rec_stride;
+  const double med_guess = c->bandwidth * log((double)(P + 1));
+  double s = 0.0;
+  for (int p = tid; p < P; p += blockDim.x) s += __ldcg(rec + (size_t)p * REC + REC_DNORM);
+  s = warp_sum(s);
+  if (lane == 0) s_red[warp] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < HD_WARPS; w++) tot += s_red[w];
+    const int stop = (a.check_early_stop && it > 0 && tot / (double)P < a.threshold) ? 1 : 0;  // SVNICP.cpp:95-101
+    s_stop = stop;
+    if (stop) { c->stop = 1; c->iters_done = it; }
+    else if (epilogue) c->iters_done = it;
+  }
+  __syncthreads();
+  if (s_stop) return;  // break BEFORE the history row of that iteration (Q9)
+  for (int i = tid; i < 6 * P; i += blockDim.x) {
+    const int comp = i / P, p = i % P;
+    const double v = __ldcg(rec + (size_t)p * REC + REC_X + comp);
+    s_x[i] = v;
+    if (it > 0 && it - 1 < a.I) a.history[(size_t)(it - 1) * 6 * P + i] = (float)v;  // SVNICP.cpp:103-107
+  }
+  if (epilogue || P < 2) return;
+  __syncthreads();
+  const unsigned long long rank0 = ((unsigned long long)P * (unsigned long long)P - 1ull) / 2ull;  // lower median
+  bool have = false;
+  double median = 0.0;
+  if (P >= 8 && it > 0 && med_guess > 0.0 && med_guess < INFINITY) {
+    const HdWindow w = hd_window(med_guess);
+    for (int i = tid; i < MED_BINS; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    hd_fast_hist(s_x, P, w, s_hist, 0, 1);
+    __syncthreads();
+    for (int i = tid; i < MED_BINS; i += blockDim.x) a.hist[i] = s_hist[i];
+    __syncthreads();
+    unsigned long long tbin = 0ull, trank = 0ull;
+    hd_select(a.hist, 0ull, rank0, MED_BINS, 13, &tbin, &trank, s_warp, s_res);
+    if (tbin != 0ull && tbin != (unsigned long long)(MED_BINS - 1)) {
+      if (tid == 0) s_cursor = 0u;
+      __syncthreads();
+      double *s_list = reinterpret_cast<double *>(s_hist);
+      hd_fast_gather(s_x, P, w, (unsigned)tbin, s_list, &s_cursor, 0, 1);
+      __syncthreads();
+      const unsigned n_c = s_cursor;
+      if (n_c >= 1u && n_c <= (unsigned)HD_COLLECT_CAP) have = hd_pick(s_list, n_c, (unsigned)(trank >> 1), &s_val, &s_found, &median);
+    }
+  }
+  if (!have) {
+    unsigned long long prefix = 0ull, rank = rank0;
+    for (int ps = 0; ps < MED_PASSES; ps++) {
+      const int nb = 1 << hd_pass_bits(ps);
+      __syncthreads();
+      for (int i = tid; i < nb; i += blockDim.x) s_hist[i] = 0u;
+      __syncthreads();
+      hd_radix_hist(s_x, P, ps, prefix, s_hist, 0, 1);
+      __syncthreads();
+      for (int i = tid; i < nb; i += blockDim.x) a.hist[i] = s_hist[i];
+      __syncthreads();
+      hd_select(a.hist, prefix, rank, nb, hd_pass_bits(ps), &prefix, &rank, s_warp, s_res);
+    }
+    median = __longlong_as_double((long long)prefix);
+  }
+  if (tid == 0) c->bandwidth = median / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -361,7 +457,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
     if (P >= 2)
       for (int t = 0; t < n_tiles; t++) {
         const int s = t % stages, k = t / stages;
-        mbar_wait(empty + s, (uint32_t)((k & 1) ^ 1));
+        mbar_wait_backoff(empty + s, (uint32_t)((k & 1) ^ 1));
         if (lane == 0) {
           mbar_expect_tx(full + s, (uint32_t)tile_bytes);
           bulk_g2s(s_dyn + (size_t)s * tile_bytes, rec + (size_t)t * TJ * REC, (uint32_t)tile_bytes, full + s);
@@ -705,6 +801,10 @@ int head_grid(int P, int sm_count) {
 }
 
 int launch_head(const SteinArgs &a, const PeerTable &pt, unsigned seq_x, int epilogue, cudaStream_t st) {
+  if (a.P <= HD_SMALL_P) {  // one CTA does the whole chain
+    k_head_small<<<1, HD_THREADS, 0, st>>>(a, pt, seq_x, epilogue);
+    return 1;
+  }
   int gp = (6 * a.P + HD_THREADS * 4 - 1) / (HD_THREADS * 4);
   if (gp < 1) gp = 1;
   if (gp > 32) gp = 32;
