@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-ldl", "-ccbin", "/usr/bin/g++"]
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl", "-ccbin", "/usr/bin/g++"]
         subprocess.check_call(cmd)
     return LIB
 

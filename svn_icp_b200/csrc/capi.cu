@@ -884,7 +884,8 @@ static int align_step(svnicp_handle h, AlignState &S) {
       h->launches += launch_stein_first(sa, st);
       h->launches += launch_update_opt(sa, sv, e + 1, st);
     } else {
-      if (overlap) CU(cudaStreamWaitEvent(st, h->ev_head, 0));  // stop flag and bandwidth of this iteration
+      // k_finalize does not wait for the head chain: it needs neither the bandwidth nor (for correctness) the stop flag -- if
+      // the stop fires concurrently it writes one more (b, H) into the record buffer of the NEXT parity, which nobody reads
       h->launches += launch_finalize(ia, pt, seq0 + (unsigned)e + 1u, st);
       PROF(4);
       if (!overlap) {
@@ -895,6 +896,7 @@ static int align_step(svnicp_handle h, AlignState &S) {
         h->launches += n;
       }
       PROF(5);
+      if (overlap) CU(cudaStreamWaitEvent(st, h->ev_head, 0));  // stop flag and bandwidth of this iteration
       h->launches += launch_tail(sa, ia, pt, seq0 + (unsigned)e + 1u, seq0 + (unsigned)e + 1u, st);
       if (overlap) CU(cudaEventRecord(h->ev_x, st));
     }
