@@ -132,16 +132,17 @@ __device__ __forceinline__ bool front_within(const MapTable &t, int cap, int slo
 
 // RemoveFarPointCloud (:93-101): count the voxels to drop
 __global__ void k_map_count_far(MapDev m, const double *pos, double r2) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s > m.slots_mask) return;
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > (size_t)m.slots_mask) return;
   if (m.tab.keys[s] == EMPTY_KEY || m.tab.count[s] == 0) return;
   if (!front_within(m.tab, m.cap, s, pos, r2, false)) atomicAdd((unsigned long long *)&m.counters[2], 1ull);
 }
 
 // ... and rebuild the survivors into the twin table (one warp per old slot: coalesced copy of the voxel's points)
 __global__ void k_map_rebuild(MapDev old, MapDev neu, const double *pos, double r2) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w > old.slots_mask) return;
+  const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // 64-bit: slots * 32 exceeds 2^32 beyond 2^27 slots
+  const int lane = threadIdx.x & 31;
+  if (w > (size_t)old.slots_mask) return;
   const unsigned long long key = old.tab.keys[w];
   const int cnt = old.tab.count[w];
   if (key == EMPTY_KEY || cnt == 0) return;
@@ -402,6 +403,8 @@ int svnicp_map_add_cloud(svnicp_map m, const void *xyz, int64_t n, int dtype_f64
   memcpy(pose + 12, t, 3 * sizeof(double));  // current_pos = new_pose.translation() (:26)
   MCU(cudaMemcpyAsync(m->d_pose, pose, sizeof(pose), cudaMemcpyHostToDevice, m->stream));
   const MapDev d = dev_view(m, m->cur);
+  // points that found no free voxel slot in THIS call (reported below; not sticky: RemoveFar may free room for the next cloud)
+  MCU(cudaMemsetAsync(m->counters + 3, 0, sizeof(long long), m->stream));
   if (n > 0) {
     const void *src = xyz;
     if (!on_device) {
@@ -421,7 +424,7 @@ int svnicp_map_add_cloud(svnicp_map m, const void *xyz, int64_t n, int dtype_f64
   MCU(cudaGetLastError());
   int rc = sync_counters(m);  // also makes the host copy safe to reuse (the caller may free xyz)
   if (rc) return rc;
-  if (m->h_counters[3] > 0) return mfail(m, SVNICP_ERR_OOM, "voxel table full: create the map with a larger capacity_voxels");
+  const long long dropped = m->h_counters[3];
   if (m->h_counters[2] > 0) {
     const int nxt = m->cur ^ 1;
     rc = clear_table(m, nxt);
@@ -434,6 +437,8 @@ int svnicp_map_add_cloud(svnicp_map m, const void *xyz, int64_t n, int dtype_f64
     rc = sync_counters(m);
     if (rc) return rc;
   }
+  // the far voxels are gone and the counters are current either way; the points that did not fit are simply not in the map
+  if (dropped > 0) return mfail(m, SVNICP_ERR_OOM, "voxel table full: some points of this cloud were dropped; create the map with a larger capacity_voxels");
   return SVNICP_OK;
 }
 
