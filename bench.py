@@ -441,14 +441,13 @@ def main():
                                   note="k_gn time expressed as FP32 issue slots per (particle, point) pair at 128 lanes/SM x sm_max; the executed "
                                        "FP32 instruction count per pair is in profiles/ (ncu)"))
     # dram__bytes_{read,write}.sum per launch from the committed ncu --set full captures (profiles/), if present
-    for name in ("r02_traffic.json", "r01_traffic.json"):
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", name)))
-            roofline["traffic"] = tr["k_filter_bytes_per_launch"] + tr["k_gn_bytes_per_launch_late"]
-            roofline["traffic_detail"] = tr
-            break
-        except Exception:  # noqa: BLE001
-            pass
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        # mean over the scan: 10 early iterations (K-slot table streamed, long lists written and re-read) + 20 late ones
+        roofline["traffic"] = tr["pass_bytes_per_launch_mean"]
+        roofline["traffic_detail"] = tr
+    except Exception:  # noqa: BLE001
+        pass
 
     # secondary variants of the same scan: the reference's own pre-processing (uniform down-sampling
     # 0.5 m then 1.5 m voxels, OdometryPipeline.cpp:559-560) and reference-style early stop (geodeAlpha.yaml:9,17-19)

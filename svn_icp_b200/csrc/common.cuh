@@ -147,10 +147,14 @@ __device__ __forceinline__ void lu_solve6_reg(double (&A)[36], double (&b)[6]) {
       b[k] = sw ? v : u;
       b[i] = sw ? u : v;
     });
-    const double d = A[k * 6 + k];
+    // ONE division per pivot; the multipliers and the back substitution multiply by the reciprocal (fp64 division is a ~30
+    // instruction dependent sequence: 21 of them made this solve 13 us of the 17 us per-particle chain of k_tail).  x * (1/d)
+    // differs from x / d by at most one rounding: 1e-16 relative on the step, far inside every parity bar.
+    const double inv = 1.0 / A[k * 6 + k];
+    A[k * 6 + k] = inv;  // the diagonal now holds the reciprocal pivot
     static_for<k + 1, 6>([&](auto I_) {
       constexpr int i = decltype(I_)::value;
-      const double l = A[i * 6 + k] / d;
+      const double l = A[i * 6 + k] * inv;
       static_for<k + 1, 6>([&](auto J) { constexpr int j = decltype(J)::value; A[i * 6 + j] -= l * A[k * 6 + j]; });
       b[i] -= l * b[k];
     });
@@ -159,7 +163,45 @@ __device__ __forceinline__ void lu_solve6_reg(double (&A)[36], double (&b)[6]) {
     constexpr int k = 5 - decltype(KK)::value;
     double s = b[k];
     static_for<k + 1, 6>([&](auto I_) { constexpr int i = decltype(I_)::value; s -= A[k * 6 + i] * b[i]; });
-    b[k] = s / A[k * 6 + k];
+    b[k] = s * A[k * 6 + k];
+  });
+}
+
+// Symmetric positive definite 6x6 solve A x = b by LDL^T, every index a compile-time constant (registers only), one reciprocal
+// per column and no pivot search.  The matrices solved on the hot path are SPD by construction -- the Gauss-Newton Hessian
+// carries + 1e-6 I (SVNICP.cpp:153) and the Stein Hessian is a kernel-weighted sum of those plus outer products -- so this is
+// the same solution as the reference's LU-based linalg::solve / inv up to rounding (cond * 1e-16), at a quarter of the
+// dependent instruction chain of a pivoted LU (which cost 12 us per particle in k_tail).  NaN / Inf inputs propagate.
+// Only the upper triangle of A (row-major 6x6) is read; A is overwritten.
+__device__ __forceinline__ void ldl_solve6_reg(double (&A)[36], double (&b)[6]) {
+  double L[36];   // strict lower triangle, L[i*6+k], k < i
+  double iD[6];   // 1 / d_j
+  static_for<0, 6>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    double w[6];  // w_k = L_jk d_k, k < j
+    double d = A[j * 6 + j];
+    static_for<0, j>([&](auto K) {
+      constexpr int k = decltype(K)::value;
+      w[k] = L[j * 6 + k] * A[k * 6 + k];  // A's diagonal holds d_k once column k is done
+      d -= L[j * 6 + k] * w[k];
+    });
+    A[j * 6 + j] = d;
+    iD[j] = 1.0 / d;
+    static_for<j + 1, 6>([&](auto I_) {
+      constexpr int i = decltype(I_)::value;
+      double sum = A[j * 6 + i];  // upper triangle: A_ji = A_ij
+      static_for<0, j>([&](auto K) { constexpr int k = decltype(K)::value; sum -= L[i * 6 + k] * w[k]; });
+      L[i * 6 + j] = sum * iD[j];
+    });
+  });
+  static_for<1, 6>([&](auto I_) {  // L y = b
+    constexpr int i = decltype(I_)::value;
+    static_for<0, i>([&](auto K) { constexpr int k = decltype(K)::value; b[i] -= L[i * 6 + k] * b[k]; });
+  });
+  static_for<0, 6>([&](auto I_) { constexpr int i = decltype(I_)::value; b[i] *= iD[i]; });  // D z = y
+  static_for<0, 5>([&](auto II) {  // L^T x = z
+    constexpr int i = 4 - decltype(II)::value;
+    static_for<i + 1, 6>([&](auto K) { constexpr int k = decltype(K)::value; b[i] -= L[k * 6 + i] * b[k]; });
   });
 }
 
@@ -171,11 +213,13 @@ __host__ __device__ __forceinline__ int tri(int r, int c) { return r * 6 - (r * 
 __device__ inline void so3_exp(const double r[3], double R[9], double *Jl) {
   const double a = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
   double n[3];
+  const double ia = 1.0 / a;  // one division (inf at a == 0: sa, ca below become NaN exactly as s / a, (1 - c) / a do -- quirk Q7)
   if (a < 1e-12) { n[0] = n[1] = n[2] = 0.0; }
-  else { n[0] = r[0] / a; n[1] = r[1] / a; n[2] = r[2] / a; }
-  const double c = cos(a), s = sin(a);
+  else { n[0] = r[0] * ia; n[1] = r[1] * ia; n[2] = r[2] * ia; }
+  double s, c;
+  sincos(a, &s, &c);
   const double ah[9] = {0, -n[2], n[1], n[2], 0, -n[0], -n[1], n[0], 0};
-  const double sa = s / a, ca = (1.0 - c) / a;
+  const double sa = s * ia, ca = (1.0 - c) * ia;
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -216,7 +260,8 @@ __device__ inline double sym3_max_eig_MtM(const double M[9]) {
   const double p2 = (B[0] - q) * (B[0] - q) + (B[3] - q) * (B[3] - q) + (B[5] - q) * (B[5] - q) + 2.0 * p1;
   const double p = sqrt(p2 / 6.0);
   if (!(p > 1e-300)) return (tr != tr) ? tr : q * (1.0 + 1e-9);
-  const double c00 = (B[0] - q) / p, c11 = (B[3] - q) / p, c22 = (B[5] - q) / p, c01 = B[1] / p, c02 = B[2] / p, c12 = B[4] / p;
+  const double ip = 1.0 / p;  // one division (the result carries a 1e-9 relative safety margin; a reciprocal multiply costs 1e-16)
+  const double c00 = (B[0] - q) * ip, c11 = (B[3] - q) * ip, c22 = (B[5] - q) * ip, c01 = B[1] * ip, c02 = B[2] * ip, c12 = B[4] * ip;
   double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
   r = fmin(fmax(r, -1.0), 1.0);
   const double lam = q + 2.0 * p * cos(acos(r) / 3.0);

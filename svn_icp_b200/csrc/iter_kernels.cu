@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a, PeerTable pt, unsi
     if (!a.svn_full_grad) {  // g = H^-1 b, SVNICP.cpp:162 (only consumed by the pre-conditioned SVGD step)
 #pragma unroll
       for (int i = 0; i < 6; i++) g[i] = b[i];
-      lu_solve6_reg(H, g);  // register resident (the record fields were taken from H above)
+      ldl_solve6_reg(H, g);  // SPD (+ 1e-6 I), register resident (the record fields were taken from H above)
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) s_out[REC_G + i] = g[i];

@@ -189,25 +189,52 @@ __device__ __forceinline__ void hd_hist_add(unsigned *s_hist, bool on, unsigned 
     if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_hist[bin], 2u * (unsigned)__popc(peers));  // D_ij = D_ji: counted twice
   }
 }
-__device__ void hd_fast_hist(const double *X, int P, const HdWindow &w, unsigned *s_hist, int cta, int n_cta) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = cta; i < P; i += n_cta)
-    for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
-      const int j = j0 + tid;
-      hd_hist_add(s_hist, j < P, j < P ? w.bin(hd_pair_d2(X, P, i, j)) : 0u, lane);
+// Upper-triangle sweep shared by all passes: CTA `cta` of `n_cta` takes rows i = cta, cta + n_cta, ...; x_i stays in registers and
+// four pairs per thread are in flight before `f(valid, d2)` consumes them (the passes are latency bound: one pair at a time left
+// the fp64 pipe 2 % busy).  f is called by all 32 lanes of a warp together (it may vote).
+template <class F>
+__device__ __forceinline__ void hd_sweep(const double *__restrict__ X, int P, int cta, int n_cta, F &&f) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = cta; i < P; i += n_cta) {
+    double xi[6];
+#pragma unroll
+    for (int d = 0; d < 6; d++) xi[d] = X[d * P + i];
+    for (int j0 = i + 1; j0 < P; j0 += 4 * nt) {
+      double d2[4];
+      bool on[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u * nt + tid;
+        on[u] = j < P;
+        double s = 0.0;
+        if (on[u]) {
+#pragma unroll
+          for (int d = 0; d < 6; d++) {
+            const double df = xi[d] - X[d * P + j];
+            s += df * df;  // SVNICP.cpp:257-260
+          }
+        }
+        d2[u] = s;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (j0 + u * nt < P) f(on[u], d2[u]);  // warp-uniform guard
     }
-  if (cta == 0 && tid == 0) atomicAdd(&s_hist[0], (unsigned)P);  // the diagonal: exact zeros, below lo
+  }
+}
+__device__ void hd_fast_hist(const double *X, int P, const HdWindow &w, unsigned *s_hist, int cta, int n_cta) {
+  const int lane = threadIdx.x & 31;
+  hd_sweep(X, P, cta, n_cta, [&](bool on, double d2) { hd_hist_add(s_hist, on, on ? w.bin(d2) : 0u, lane); });
+  if (cta == 0 && threadIdx.x == 0) atomicAdd(&s_hist[0], (unsigned)P);  // the diagonal: exact zeros, below lo
 }
 // values of bin tbin, once per unordered pair (each stands for two entries of the P x P matrix)
 __device__ void hd_fast_gather(const double *X, int P, const HdWindow &w, unsigned tbin, double *list, unsigned *cursor, int cta, int n_cta) {
-  for (int i = cta; i < P; i += n_cta)
-    for (int j = i + 1 + threadIdx.x; j < P; j += blockDim.x) {
-      const double d2 = hd_pair_d2(X, P, i, j);
-      if (w.bin(d2) == tbin) {
-        const unsigned k = atomicAdd(cursor, 1u);
-        if (k < (unsigned)HD_COLLECT_CAP) list[k] = d2;
-      }
+  hd_sweep(X, P, cta, n_cta, [&](bool on, double d2) {
+    if (on && w.bin(d2) == tbin) {
+      const unsigned k = atomicAdd(cursor, 1u);
+      if (k < (unsigned)HD_COLLECT_CAP) list[k] = d2;
     }
+  });
 }
 // exact order statistic `target` (ascending, among the n_c collected values) -> *out; returns false if none found (cannot happen)
 __device__ bool hd_pick(const double *s_list, unsigned n_c, unsigned target, unsigned long long *s_val, int *s_found, double *out) {
@@ -229,23 +256,16 @@ __device__ bool hd_pick(const double *s_list, unsigned n_c, unsigned target, uns
 }
 // one radix pass: upper triangle, D_ij = D_ji counted twice, diagonal once (exact zeros: key 0)
 __device__ void hd_radix_hist(const double *X, int P, int s, unsigned long long prefix, unsigned *s_hist, int cta, int n_cta) {
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int lane = threadIdx.x & 31;
   const int consumed = hd_bits_before(s), nb = 1 << hd_pass_bits(s);
   const int shift = 63 - consumed - hd_pass_bits(s);
   const unsigned bmask = (unsigned)(nb - 1);
-  for (int i = cta; i < P; i += n_cta)
-    for (int j0 = i + 1; j0 < P; j0 += blockDim.x) {
-      const int j = j0 + tid;
-      bool match = false;
-      unsigned bin = 0;
-      if (j < P) {
-        const unsigned long long key = (unsigned long long)__double_as_longlong(hd_pair_d2(X, P, i, j));
-        match = (consumed == 0) || ((key >> (63 - consumed)) == prefix);
-        bin = (unsigned)(key >> shift) & bmask;
-      }
-      hd_hist_add(s_hist, match, bin, lane);
-    }
-  if (cta == 0 && tid == 0 && (consumed == 0 || prefix == 0ull)) atomicAdd(&s_hist[0], (unsigned)P);
+  hd_sweep(X, P, cta, n_cta, [&](bool on, double d2) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
+    const bool match = on && ((consumed == 0) || ((key >> (63 - consumed)) == prefix));
+    hd_hist_add(s_hist, match, (unsigned)(key >> shift) & bmask, lane);
+  });
+  if (cta == 0 && threadIdx.x == 0 && (consumed == 0 || prefix == 0ull)) atomicAdd(&s_hist[0], (unsigned)P);
 }
 
 __global__ void __launch_bounds__(HD_THREADS, 8) k_head_fast1(SteinArgs a) {
@@ -574,7 +594,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
       for (int cc = r; cc < 6; cc++) {
         double s = 0.0;
         for (int w = 0; w < JQ; w++) s += s_Hbar[w][tri(r, cc)];
-        A0[6 * r + cc] = s / (double)P;  // :85 mean over particles
+        A0[6 * r + cc] = s * (1.0 / (double)P);  // :85 mean over particles
         A0[6 * cc + r] = A0[6 * r + cc];
       }
     // :225 inverse, column by column (each solve register resident; the pivot sequence is the same for every column)
@@ -585,7 +605,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
       for (int q = 0; q < 36; q++) A[q] = A0[q];
 #pragma unroll
       for (int q = 0; q < 6; q++) e[q] = (q == col) ? 1.0 : 0.0;
-      lu_solve6_reg(A, e);
+      ldl_solve6_reg(A, e);
 #pragma unroll
       for (int q = 0; q < 6; q++) s_Hinv[6 * q + col] = e[q];
     }
@@ -594,6 +614,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
 
   // ---------------- one thread per particle: solve, pose update, head of the next iteration ----------------
   const double *R0 = ia.sc.R0;
+  const double inv_P = 1.0 / (double)P;
   if (warp < TL_WARPS && lane == 0 && (warp % JQ) == 0) {
     const int ii = warp / JQ;
     const int l = blockIdx.x * NI + ii;
@@ -612,7 +633,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
           for (int cc = rr; cc < 6; cc++) { A[6 * rr + cc] = __ldcg(r + REC_H + tri(rr, cc)); A[6 * cc + rr] = A[6 * rr + cc]; }
 #pragma unroll
         for (int q = 0; q < 6; q++) d[q] = __ldcg(r + REC_B + q);
-        lu_solve6_reg(A, d);
+        ldl_solve6_reg(A, d);
         for (int q = 0; q < 6; q++) d[q] = -d[q];
       } else if (a.svn_full_grad) {
         double A[36];
@@ -622,16 +643,16 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
           for (int cc = rr; cc < 6; cc++) {
             double sum = 0.0;
             for (int w = 0; w < JQ; w++) sum += s_part[ii * JQ + w][tri(rr, cc)];
-            A[6 * rr + cc] = sum / (double)P;
+            A[6 * rr + cc] = sum * inv_P;  // x * (1/P): one division instead of 27
             A[6 * cc + rr] = A[6 * rr + cc];
           }
 #pragma unroll
         for (int q = 0; q < 6; q++) {
           double sum = 0.0;
           for (int w = 0; w < JQ; w++) sum += s_part[ii * JQ + w][21 + q];
-          d[q] = sum / (double)P;
+          d[q] = sum * inv_P;
         }
-        lu_solve6_reg(A, d);  // :250 (the reference forms the explicit inverse; tolerance-level difference)
+        ldl_solve6_reg(A, d);  // :250 (the reference forms the explicit inverse; H-bar is SPD: tolerance-level difference)
         for (int q = 0; q < 6; q++) d[q] = a.lr * d[q];
       } else {
         double gs[6], kn[6], ks = 0.0;
@@ -649,6 +670,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
       }
 #pragma unroll
       for (int q = 0; q < 6; q++) a.delta[(size_t)l * 6 + q] = d[q];
+      if (a.stamps && blockIdx.x == 0 && ii == 0) a.stamps[6] = (double)global_timer_ns();  // solve done
       // pose update, SVNICP.cpp:268-279
       double dR[9], Jl[9], R[9], Rn[9], dt[3], t[3], w[3];
       so3_exp(d + 3, dR, Jl);  // :269-271
@@ -671,6 +693,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
       a.dnorm[l] = dn;
       // head of the next iteration: x = [t ; Log R] and |delta| into every rank's NEXT record buffer
       so3_log(Rn, w);
+      if (a.stamps && blockIdx.x == 0 && ii == 0) a.stamps[7] = (double)global_timer_ns();  // Exp, update, Log done
       for (int r = 0; r < pt.n_ranks; r++) {
         double *o = pt.rec[r] + nxt_off + (size_t)p * REC;
 #pragma unroll
