@@ -435,6 +435,10 @@ constexpr int TL_THREADS = TL_CONSUMERS + 32;  // + one producer warp (bulk TMA)
 constexpr int TL_ENV_CHUNK = 1024;             // particles per pass of the envelope reduction (last CTA)
 
 // dynamic shared memory: [stages][tile_records * REC] doubles, then the mbarriers
+// MODE: 0 = single particle (Gauss-Newton step), 1 = full SVN, 2 = pre-conditioned SVGD.  A template parameter, not a run-time
+// branch: each instantiation carries only its own code (the three modes together were 15k instructions, and the single-thread
+// sections of this kernel run cold -- instruction fetch is what they cost)
+template <int MODE>
 __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia, PeerTable pt, unsigned seq_h, unsigned seq_x_out, int NI,
                                                         int JQ, int stages) {
   Ctrl *c = a.ctrl;
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
 
   if (warp == TL_WARPS) {
     // ---------------- producer warp: AoS record tiles, one bulk copy each ----------------
-    if (P >= 2)
+    if (MODE != 0)
       for (int t = 0; t < n_tiles; t++) {
         const int s = t % stages, k = t / stages;
         mbar_wait_backoff(empty + s, (uint32_t)((k & 1) ^ 1));
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
     double xi[6];
 #pragma unroll
     for (int d = 0; d < 6; d++) xi[d] = __ldcg(rec + (size_t)i * REC + REC_X + d);
-    if (P >= 2 && a.svn_full_grad) {
+    if constexpr (MODE == 1) {
       double Hm[21], v[6];
 #pragma unroll
       for (int q = 0; q < 21; q++) Hm[q] = 0.0;
@@ -536,7 +540,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
 #pragma unroll
         for (int q = 0; q < 6; q++) s_part[warp][21 + q] = v[q];
       }
-    } else if (P >= 2) {
+    } else if constexpr (MODE == 2) {
       // pre-conditioned SVGD (SVNICP.cpp:85, :218-227); the warps of particle 0 of the CTA also sum H over all j (mean Hessian)
       double gs[6], kn[6], ks = 0.0, Hs[21];
 #pragma unroll
@@ -586,7 +590,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
   }
   __syncthreads();
   if (blockIdx.x == 0) TL_STAMP(2);
-  if (P >= 2 && !a.svn_full_grad && tid == 0) {
+  if (MODE == 2 && tid == 0) {
     double A0[36];
 #pragma unroll
     for (int r = 0; r < 6; r++)
@@ -597,8 +601,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
         A0[6 * r + cc] = s * (1.0 / (double)P);  // :85 mean over particles
         A0[6 * cc + r] = A0[6 * r + cc];
       }
-    // :225 inverse, column by column (each solve register resident; the pivot sequence is the same for every column)
-#pragma unroll
+    // :225 inverse, column by column; the loop stays rolled (six unrolled solves were 1800 instructions of cold code on the
+    // critical path of every CTA -- instruction fetch, not arithmetic, is what this single-thread section costs)
+#pragma unroll 1
     for (int col = 0; col < 6; col++) {
       double A[36], e[6];
 #pragma unroll
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
       for (int q = 0; q < 6; q++) s_Hinv[6 * q + col] = e[q];
     }
   }
-  if (P >= 2 && !a.svn_full_grad) __syncthreads();
+  if (MODE == 2) __syncthreads();
 
   // ---------------- one thread per particle: solve, pose update, head of the next iteration ----------------
   const double *R0 = ia.sc.R0;
@@ -624,7 +629,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
     if (ii < NI && l < a.P_l) {
       const int p = a.p_lo + l;
       double d[6];
-      if (P < 2) {  // SVNICP.cpp:88-89
+      if constexpr (MODE == 0) {  // SVNICP.cpp:88-89
         double A[36];
         const double *r = rec + (size_t)p * REC;
 #pragma unroll
@@ -635,7 +640,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
         for (int q = 0; q < 6; q++) d[q] = __ldcg(r + REC_B + q);
         ldl_solve6_reg(A, d);
         for (int q = 0; q < 6; q++) d[q] = -d[q];
-      } else if (a.svn_full_grad) {
+      } else if constexpr (MODE == 1) {
         double A[36];
 #pragma unroll
         for (int rr = 0; rr < 6; rr++)
@@ -861,14 +866,23 @@ void tail_shape(int P_l, int sm_count, int *NI, int *JQ, int *stages, size_t *sm
 }
 
 int launch_tail(const SteinArgs &a, const IterArgs &ia, const PeerTable &pt, unsigned seq_h, unsigned seq_x_out, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  static unsigned long long attr_set = 0ull;  // per device (the attribute belongs to the device's copy of the function)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_set >> (dev & 63)) & 1ull)) {
+    cudaFuncSetAttribute(k_tail<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_tail<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_tail<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set |= 1ull << (dev & 63);
+  }
   int NI, JQ, stages;
   size_t smem;
   tail_shape(a.P_l, a.sm_count, &NI, &JQ, &stages, &smem);
   const int grid = (a.P_l + NI - 1) / NI;
   if (grid < 1) return 0;
-  k_tail<<<grid, TL_THREADS, smem, st>>>(a, ia, pt, seq_h, seq_x_out, NI, JQ, stages);
+  if (a.P < 2) k_tail<0><<<grid, TL_THREADS, smem, st>>>(a, ia, pt, seq_h, seq_x_out, NI, JQ, stages);
+  else if (a.svn_full_grad) k_tail<1><<<grid, TL_THREADS, smem, st>>>(a, ia, pt, seq_h, seq_x_out, NI, JQ, stages);
+  else k_tail<2><<<grid, TL_THREADS, smem, st>>>(a, ia, pt, seq_h, seq_x_out, NI, JQ, stages);
   return 1;
 }
 
