@@ -150,7 +150,7 @@ struct svnicp_handle_t {
   std::vector<cudaEvent_t> prof_events;  // 7 per iteration
   double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // prep, filter, gn, finalize, gather, stein(decide+median+stein+update), setup, iterations executed
   // launch shape
-  int TB = 16, stages = 3, n_slices = 1, n_pgroups = 1, PG = 256, RG = 1;
+  int TB = 16, stages = 3, n_slices = 1, n_pgroups = 1, PG = 512, RG = 1;
   size_t gn_smem = 0;
 };
 
@@ -545,19 +545,22 @@ static int choose_shape(svnicp_handle h) {
   h->Kp = Kp;
   int TB = 32;
   int S = 3;
-  size_t budget = 100 * 1024;  // two CTAs of k_gn per SM (registers allow no more: measured)
+  // one CTA of k_gn per SM: its tile ring may take ~100 KB next to the 64 KB of second-level accumulators, which leaves room
+  // for the small side-stream kernels (k_head_*, 33 KB) on the same SM
+  size_t budget = 100 * 1024;
   if (h->prm.gn_stages > 1) S = h->prm.gn_stages;  // tuning knobs (svnicp_params extensions, bench sweeps)
-  if (h->prm.gn_smem_kb > 0) budget = (size_t)h->prm.gn_smem_kb * 1024;
-  const int consumers = 256;
+  if (h->prm.gn_smem_kb > 0) budget = (size_t)(h->prm.gn_smem_kb < 150 ? h->prm.gn_smem_kb : 150) * 1024;
+  const int consumers = GN_CONSUMERS;  // every consumer thread of k_gn carries two particles (packed fp32 pairs)
   while (TB > 4 && gn_stage_bytes(TB, Kp) * S > budget) TB >>= 1;
   h->TB = TB;
   h->stages = S;
-  h->gn_smem = gn_stage_bytes(TB, Kp) * S + 2 * S * sizeof(uint64_t) + 128;
-  int PG = 1;
-  while (PG < h->P_l && PG < consumers) PG <<= 1;
+  h->gn_smem = gn_smem_bytes(TB, Kp, S);
+  const int pairs = (h->P_l + 1) / 2;
+  int PG = 1;  // particle pairs (threads) per row group
+  while (PG < pairs && PG < consumers) PG <<= 1;
   h->PG = PG;
   h->RG = consumers / PG;
-  h->n_pgroups = (h->P_l + PG - 1) / PG;
+  h->n_pgroups = (pairs + PG - 1) / PG;
   if (h->n_pgroups < 1) h->n_pgroups = 1;
   return SVNICP_OK;
 }
@@ -602,7 +605,7 @@ static int prepare_scan(svnicp_handle h) {
   CU(h->sidx.ensure((size_t)n_t));
   CU(h->sxyz.ensure((size_t)3 * n_t));
   const int n_tiles = n_pad / TB;
-  int n_slices = (2 * h->sm_count) / h->n_pgroups;
+  int n_slices = h->sm_count / h->n_pgroups;  // one CTA of k_gn per SM
   if (n_slices < 1) n_slices = 1;
   if (n_slices > n_tiles) n_slices = n_tiles;
   h->n_slices = n_slices;

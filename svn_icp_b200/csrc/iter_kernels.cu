@@ -398,21 +398,12 @@ __global__ void __launch_bounds__(256, 4) k_filter_reuse(IterArgs a) {
 // ---------------------------------------------------------------------------------------------
 // k_gn: fused transform + 1-NN + robust weight + Gauss-Newton reduction
 // ---------------------------------------------------------------------------------------------
-constexpr int GN_CONSUMERS = 256;
-constexpr int GN_THREADS = GN_CONSUMERS + 32;
 constexpr int GN_FLUSH_ROWS = 32;
-// Three-level accumulation of the 16 Gauss-Newton sums: fp32 over GN_FLUSH_ROWS rows -> accum2_t registers over
-// GN_FLUSH2 such flushes -> the thread's fp64 partial slot.  fp32 second level: measured 30.3 vs 35.5 ms per scan at
-// configs[1] against an fp64 second level (-DSVN_GN_ACC2_FP64), at <= ~5e-7 relative error in H and b.
+// Three-level accumulation of the 16 Gauss-Newton sums: fp32 registers over GN_FLUSH_ROWS rows -> fp32 in shared memory (the
+// thread's own 16 slots: 32 registers less per thread, which is what lets 16 consumer warps share an SM) over GN_FLUSH2 such
+// flushes -> the thread's fp64 partial slot.  fp32 second level: measured 30.3 vs 35.5 ms per scan at configs[1] against an
+// fp64 second level (round 1), at <= ~5e-7 relative error in H and b.
 constexpr int GN_FLUSH2 = 64;
-#ifdef SVN_GN_ACC2_FP64
-typedef double accum2_t;
-#else
-typedef float accum2_t;
-#endif
-#ifndef SVN_GN_MINBLOCKS
-#define SVN_GN_MINBLOCKS 2
-#endif
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
@@ -425,6 +416,59 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): one instruction issues the same IEEE-rn operation on two independent
+// floats held in an aligned register pair.  The FMA pipe retires the same 128 results/clk/SM either way
+// (scripts/ubench/ffma2.cu), but k_gn is bound by instruction ISSUE (75 % issue-slot use at 50 % FMA-pipe use with scalar
+// code): a thread that carries two particles needs one issue slot per two flops, and every per-row operand (source point,
+// candidate) enters as a broadcast register (`R.F32` operand form: no packing instruction).  Each half is rounded exactly as
+// the scalar instruction would round it, so the correspondence indices stay bit-exact.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float lo(f2 v) { float a; asm("{ .reg .f32 t; mov.b64 {%0, t}, %1; }" : "=f"(a) : "l"(v)); return a; }
+__device__ __forceinline__ float hi(f2 v) { float a; asm("{ .reg .f32 t; mov.b64 {t, %0}, %1; }" : "=f"(a) : "l"(v)); return a; }
+__device__ __forceinline__ f2 bc(float s) { return pk(s, s); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 neg2(f2 a) { return pk(-lo(a), -hi(a)); }  // folds into the operand's negate modifier
+__device__ __forceinline__ f2 sel2(bool p0, bool p1, f2 a, f2 b) { return pk(p0 ? lo(a) : lo(b), p1 ? hi(a) : hi(b)); }
+__device__ __forceinline__ f2 min4_2(f2 a, f2 b, f2 c, f2 d) {  // fminf drops NaN, like a strict '<' against +inf
+  return pk(fminf(fminf(lo(a), lo(b)), fminf(lo(c), lo(d))), fminf(fminf(hi(a), hi(b)), fminf(hi(c), hi(d))));
+}
+
+// parity tap (debug_corr handles only): the slot of the winner in the un-pruned table = first slot with identical coordinates
+__device__ __noinline__ void gn_dbg_tap(const IterArgs &a, int row, int l, float qx, float qy, float qz, float ex, float ey, float ez, bool valid) {
+  const float4 *full_row = a.cand + (size_t)row * a.K;
+  const float wx_ = __fsub_rn(qx, ex), wy_ = __fsub_rn(qy, ey), wz_ = __fsub_rn(qz, ez);
+  int slot = 0;
+  float bd_ = INFINITY;
+  for (int kk = 0; kk < a.K; kk++) {  // q - (q - c) is c up to one rounding: take the nearest table entry
+    const float4 f = full_row[kk];
+    const float dd_ = fabsf(f.x - wx_) + fabsf(f.y - wy_) + fabsf(f.z - wz_);
+    if (dd_ < bd_) { bd_ = dd_; slot = kk; }
+  }
+  a.dbg_idx[(size_t)l * a.n_s + row] = a.cand_idx[(size_t)row * a.K + slot];
+  a.dbg_mask[(size_t)l * a.n_s + row] = valid ? 1 : 0;
+}
+
+// long lists, one particle: the first slot of chunk [bk, bk+4) whose distance IS the minimum -- what slot-by-slot strict '<'
+// would have kept.  Scalar, once per row; operation order as in SVN_DIST.
+__device__ __forceinline__ void gn_recover(const float4 *e, int bk, float qx, float qy, float qz, float best, float &ex, float &ey, float &ez) {
+  const float4 c0 = e[bk], c1 = e[bk + 1], c2 = e[bk + 2], c3 = e[bk + 3];
+#define SVN_D1(C, T)                                                                                      \
+  const float T##x = __fsub_rn(qx, (C).x), T##y = __fsub_rn(qy, (C).y), T##z = __fsub_rn(qz, (C).z);       \
+  const float T##d = __fmaf_rn(T##z, T##z, __fmaf_rn(T##y, T##y, __fmul_rn(T##x, T##x)));
+  SVN_D1(c0, u) SVN_D1(c1, v) SVN_D1(c2, w) SVN_D1(c3, z)
+#undef SVN_D1
+  (void)zd;
+  const bool h0 = ud == best, h1 = vd == best, h2 = wd == best;
+  ex = h0 ? ux : h1 ? vx : h2 ? wx : zx;
+  ey = h0 ? uy : h1 ? vy : h2 ? wy : zy;
+  ez = h0 ? uz : h1 ? vz : h2 ? wz : zz;
+  if (best == INFINITY) { ex = ux; ey = uy; ez = uz; }  // nothing compared below +inf (NaN query): slot 0
+}
+
 // UNI: every lane of a warp works on the same source point (PG >= 32) -> the early exit is a warp vote.
 // FIRST: first-order mode of the SVGD-ICP class (SVGDICP::sgd_grad, SVGDICP.cpp:398-455): sum 0 counts the unmasked
 // pairs (nonzero_count, :404) and the second-moment sums 1..9 are not needed -- the gradient is E and C alone because
@@ -433,8 +477,10 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // length << 16 | true length; 0 = padding row), then three 32-bit row masks written by the producer warp: rows whose padded list
 // length is 2, 4, and more.  The consumers walk the three classes one after the other with a loop body specialised for the
 // class (no data-dependent branch inside the two short-list bodies: control flow was 18 of 122 instructions per row).
+// Thread -> particles: consumer thread pl of particle group y carries particles 2*(y*PG + pl) and the next one (neighbours in
+// the pose-space ordering of the slice: their scan lengths are similar); .x of every pair is the even particle.
 template <bool DBG, bool UNI, bool FIRST>
-__global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a) {  // (.., 3) spills the fp64 accumulators: measured slower
+__global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps x 128 registers
   if (a.ctrl->stop) return;
   extern __shared__ __align__(128) unsigned char smem[];
   const int TB = a.TB, Kp = a.Kp, S = a.stages;
@@ -453,111 +499,116 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
   }
   __syncthreads();
 
-  if (warp == GN_CONSUMERS / 32) {
-    // ---------------- producer warp: 1-D TMA bulk copies of the pruned lists + the row-class masks ----------------
-    for (int i = 0; i < n_my; i++) {
-      const int s = i % S, k = i / S;
-      mbar_wait_backoff(empty + s, (uint32_t)((k & 1) ^ 1));
-      const int row0 = (slice + i * n_slices) * TB;
-      unsigned char *st = smem + (size_t)s * stage_bytes;
-      const int cnt = (lane < TB) ? (__float_as_int(a.hdr[row0 + lane].w) >> 16) : 0;
-      const unsigned m2 = __ballot_sync(0xffffffffu, cnt == 2), m4 = __ballot_sync(0xffffffffu, cnt == 4), ml = __ballot_sync(0xffffffffu, cnt > 4);
-      int bytes = cnt * 16;
-      int total = bytes;
+  // ---------------- tile loads: 1-D TMA bulk copies of the pruned lists + the row-class masks ----------------
+  // There is no producer warp (a 17th warp would round the CTA's register allocation up to 20 warps: 96 registers per
+  // thread).  The warps take turns instead: at tile i, warp i % 16 refills the stage that tile i-1 has just left with tile
+  // i+S-1; it fetched that tile's list lengths one tile earlier, so the only wait it adds is for the slowest warp's tile i-1.
+  constexpr int NW = GN_CONSUMERS / 32;
+  auto tile_cnt = [&](int j) -> int {  // padded list length of row `lane` of this CTA's j-th tile
+    return (lane < TB) ? (__float_as_int(__ldg(&a.hdr[(size_t)(slice + j * n_slices) * TB + lane].w)) >> 16) : 0;
+  };
+  auto tile_issue = [&](int j, int cnt) {  // whole warp
+    const int s = j % S;
+    const int row0 = (slice + j * n_slices) * TB;
+    unsigned char *st = smem + (size_t)s * stage_bytes;
+    const unsigned m2 = __ballot_sync(0xffffffffu, cnt == 2), m4 = __ballot_sync(0xffffffffu, cnt == 4), ml = __ballot_sync(0xffffffffu, cnt > 4);
+    const int bytes = cnt * 16;
+    int total = bytes;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      total += TB * 16;
-      if (lane == 0) {
-        unsigned *msk = reinterpret_cast<unsigned *>(st + msk_off);
-        msk[0] = m2; msk[1] = m4; msk[2] = ml;
-        mbar_expect_tx(full + s, (uint32_t)total);  // arrive = release: the masks are visible to whoever sees the phase complete
-      }
-      __syncwarp();
-      if (lane < TB && cnt > 0) bulk_g2s(st + (size_t)lane * Kp * 16, a.clist + (size_t)(row0 + lane) * Kp, (uint32_t)bytes, full + s);
-      if (lane == 0) bulk_g2s(st + hdr_off, a.hdr + row0, (uint32_t)(TB * 16), full + s);
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    total += TB * 16;
+    if (lane == 0) {
+      unsigned *msk = reinterpret_cast<unsigned *>(st + msk_off);
+      msk[0] = m2; msk[1] = m4; msk[2] = ml;
+      mbar_expect_tx(full + s, (uint32_t)total);  // arrive = release: the masks are visible to whoever sees the phase complete
     }
-    return;
-  }
+    __syncwarp();
+    if (lane < TB && cnt > 0) bulk_g2s(st + (size_t)lane * Kp * 16, a.clist + (size_t)(row0 + lane) * Kp, (uint32_t)bytes, full + s);
+    if (lane == 0) bulk_g2s(st + hdr_off, a.hdr + row0, (uint32_t)(TB * 16), full + s);
+  };
+  for (int j = 0; j < S - 1 && j < n_my; j++)
+    if (warp == j % NW) tile_issue(j, tile_cnt(j));
+  int cnt_pref = (warp == 0 && S - 1 < n_my) ? tile_cnt(S - 1) : 0;
 
-  // ---------------- consumers: one thread = one particle (x RG row groups) ----------------
-  const int PG = a.PG, RG = a.RG;
+  // ---------------- consumers: one thread = two particles (x RG row groups) ----------------
+  const int PG = a.PG, RG = a.RG;  // PG = consumer threads (particle PAIRS) per row group
   const int pl = tid % PG, rg = tid / PG;
-  const int l = blockIdx.y * PG + pl;  // local particle index
-  const bool active = l < a.P_l;
-  float A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, A6 = 0, A7 = 0, A8 = 0, t0 = 0, t1 = 0, t2 = 0;
+  const int l0 = 2 * (blockIdx.y * PG + pl), l1 = l0 + 1;  // local particle indices
+  const bool active = l0 < a.P_l, active1 = l1 < a.P_l;
+  f2 A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, A6 = 0, A7 = 0, A8 = 0, t0 = 0, t1 = 0, t2 = 0;
   if (active) {
-    const float *xf = a.xf + (size_t)l * 12;
-    A0 = xf[0]; A1 = xf[1]; A2 = xf[2]; A3 = xf[3]; A4 = xf[4]; A5 = xf[5]; A6 = xf[6]; A7 = xf[7]; A8 = xf[8];
-    t0 = xf[9]; t1 = xf[10]; t2 = xf[11];
+    const float *xa = a.xf + (size_t)l0 * 12, *xb = a.xf + (size_t)(active1 ? l1 : l0) * 12;  // an odd tail pairs with itself
+    A0 = pk(xa[0], xb[0]); A1 = pk(xa[1], xb[1]); A2 = pk(xa[2], xb[2]); A3 = pk(xa[3], xb[3]); A4 = pk(xa[4], xb[4]);
+    A5 = pk(xa[5], xb[5]); A6 = pk(xa[6], xb[6]); A7 = pk(xa[7], xb[7]); A8 = pk(xa[8], xb[8]);
+    t0 = pk(xa[9], xb[9]); t1 = pk(xa[10], xb[10]); t2 = pk(xa[11], xb[11]);
   }
   const float Dm = a.max_dist;
-  float acc[NACC];
-  accum2_t dacc[NACC];  // second-level accumulators (see SVN_GN_ACC2_FP32)
+  f2 acc[NACC];  // first accumulation level, both particles
+  f2 *dacc = reinterpret_cast<f2 *>(smem + gn_dacc_offset(TB, Kp, S)) + tid;  // second level: slot j at dacc[j * GN_CONSUMERS]
 #pragma unroll
-  for (int i = 0; i < NACC; i++) { acc[i] = 0.f; dacc[i] = 0; }
+  for (int i = 0; i < NACC; i++) { acc[i] = 0; dacc[i * GN_CONSUMERS] = 0; }
   int rows_in_acc = 0, flushes2 = 0;
   bool wrote = false;
-  double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + (active ? l : 0)) * NACC;
+  double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + (active ? l0 : 0)) * NACC;  // particle l1: out + NACC
   // rows of a tile this thread owns: r = rg, rg + RG, ... (RG is a power of two dividing TB or larger than it)
   unsigned rgmask = 0;
   for (int r = rg; r < TB; r += RG) rgmask |= 1u << r;
 
 // a = A' s' ; q = a + tau : query relative to q0_b.  Order fixed (index parity with oracle_corr_f32).
-#define SVN_QUERY                                                                                      \
-  const float ax = __fmaf_rn(A0, sv.x, __fmaf_rn(A1, sv.y, __fmul_rn(A2, sv.z)));                      \
-  const float ay = __fmaf_rn(A3, sv.x, __fmaf_rn(A4, sv.y, __fmul_rn(A5, sv.z)));                      \
-  const float az = __fmaf_rn(A6, sv.x, __fmaf_rn(A7, sv.y, __fmul_rn(A8, sv.z)));                      \
-  const float qx = __fadd_rn(ax, t0), qy = __fadd_rn(ay, t1), qz = __fadd_rn(az, t2);
+#define SVN_QUERY                                                                 \
+  const f2 sx = bc(sv.x), sy = bc(sv.y), sz = bc(sv.z);                           \
+  const f2 ax = fma2(A0, sx, fma2(A1, sy, mul2(A2, sz)));                         \
+  const f2 ay = fma2(A3, sx, fma2(A4, sy, mul2(A5, sz)));                         \
+  const f2 az = fma2(A6, sx, fma2(A7, sy, mul2(A8, sz)));                         \
+  const f2 qx = add2(ax, t0), qy = add2(ay, t1), qz = add2(az, t2);
 // residual and squared distance to one candidate: fixed operation order (index parity)
-#define SVN_DIST(C, T)                                                                                                       \
-  const float T##x = __fsub_rn(qx, (C).x), T##y = __fsub_rn(qy, (C).y), T##z = __fsub_rn(qz, (C).z);                          \
-  const float T##d = __fmaf_rn(T##z, T##z, __fmaf_rn(T##y, T##y, __fmul_rn(T##x, T##x)));
-// robust weight + the 16 Gauss-Newton sums for the matched pair (residual ex, ey, ez, squared distance best).
+#define SVN_DIST(C, T)                                                                                    \
+  const f2 T##x = sub2(qx, bc((C).x)), T##y = sub2(qy, bc((C).y)), T##z = sub2(qz, bc((C).z));            \
+  const f2 T##d = fma2(T##z, T##z, fma2(T##y, T##y, mul2(T##x, T##x)));
+// robust weight + the 16 Gauss-Newton sums for the matched pairs (residual ex, ey, ez, squared distance best: packed).
 // LIVE = false turns the row into a no-op (the phantom second row of an odd-sized pair, see the two-candidate class).
 #define SVN_ACCUM(LIVE)                                                                                                      \
   {                                                                                                                          \
-    const bool valid = best < Dm; /* SVGDICP.cpp:332: squared distance vs un-squared max_dist (Q1) */                        \
+    const float b0_ = lo(best), b1_ = hi(best);                                                                              \
+    const bool v0_ = b0_ < Dm, v1_ = b1_ < Dm; /* SVGDICP.cpp:332: squared distance vs un-squared max_dist (Q1) */           \
     if (DBG) {                                                                                                               \
-      if (active && (LIVE)) {                                                                                                        \
-        /* recover the slot of the winner in the un-pruned table (first slot with identical coordinates) */                  \
-        const int row = (slice + i * n_slices) * TB + r;                                                                     \
-        const float4 *full_row = a.cand + (size_t)row * a.K;                                                                 \
-        const float wx_ = __fsub_rn(qx, ex) , wy_ = __fsub_rn(qy, ey), wz_ = __fsub_rn(qz, ez);                              \
-        int slot = 0;                                                                                                        \
-        float bd_ = INFINITY;                                                                                                \
-        for (int kk = 0; kk < a.K; kk++) { /* q - (q - c) is c up to one rounding: take the nearest table entry */            \
-          const float4 f = full_row[kk];                                                                                     \
-          const float dd_ = fabsf(f.x - wx_) + fabsf(f.y - wy_) + fabsf(f.z - wz_);                                          \
-          if (dd_ < bd_) { bd_ = dd_; slot = kk; }                                                                           \
-        }                                                                                                                    \
-        a.dbg_idx[(size_t)l * a.n_s + row] = a.cand_idx[(size_t)row * a.K + slot];                                           \
-        a.dbg_mask[(size_t)l * a.n_s + row] = valid ? 1 : 0;                                                                 \
-      }                                                                                                                      \
+      const int row = (slice + i * n_slices) * TB + r;                                                                       \
+      if (active && (LIVE)) gn_dbg_tap(a, row, l0, lo(qx), lo(qy), lo(qz), lo(ex), lo(ey), lo(ez), v0_);                      \
+      if (active1 && (LIVE)) gn_dbg_tap(a, row, l1, hi(qx), hi(qy), hi(qz), hi(ex), hi(ey), hi(ez), v1_);                     \
     }                                                                                                                        \
     /* rho = (D / (D + 3 |e|))^2  (SVNICP.cpp:120-122); masked pairs: rho' = 0 and +1 on the translation block (Q2) */       \
-    const float en = sqrt_approx(best);                                                                                      \
-    const float wq = Dm * rcp_approx(fmaf(3.0f, en, Dm));                                                                    \
-    const float rho = wq * wq;                                                                                               \
-    const float rp = (valid && (LIVE)) ? rho : 0.0f;                                                                         \
+    const f2 en = pk(sqrt_approx(b0_), sqrt_approx(b1_));                                                                    \
+    const f2 den = fma2(bc(3.0f), en, bc(Dm));                                                                               \
+    const f2 wq = mul2(bc(Dm), pk(rcp_approx(lo(den)), rcp_approx(hi(den))));                                                \
+    const f2 rho = mul2(wq, wq);                                                                                             \
+    const f2 rp = pk((v0_ && (LIVE)) ? lo(rho) : 0.0f, (v1_ && (LIVE)) ? hi(rho) : 0.0f);                                    \
     if (FIRST) {                                                                                                             \
-      acc[0] += (valid && (LIVE)) ? 1.0f : 0.0f;                                                                             \
+      acc[0] = add2(acc[0], pk((v0_ && (LIVE)) ? 1.0f : 0.0f, (v1_ && (LIVE)) ? 1.0f : 0.0f));                               \
     } else {                                                                                                                 \
-      acc[0] += (LIVE) ? (valid ? rho : 1.0f) : 0.0f;                                                                                        \
-      const float gx = rp * sv.x, gy = rp * sv.y, gz = rp * sv.z;                                                            \
-      acc[1] += gx; acc[2] += gy; acc[3] += gz;                                                                              \
-      acc[4] = fmaf(gx, sv.x, acc[4]); acc[5] = fmaf(gx, sv.y, acc[5]); acc[6] = fmaf(gx, sv.z, acc[6]);                     \
-      acc[7] = fmaf(gy, sv.y, acc[7]); acc[8] = fmaf(gy, sv.z, acc[8]); acc[9] = fmaf(gz, sv.z, acc[9]);                     \
+      acc[0] = add2(acc[0], pk((LIVE) ? (v0_ ? lo(rho) : 1.0f) : 0.0f, (LIVE) ? (v1_ ? hi(rho) : 1.0f) : 0.0f));             \
+      const f2 gx = mul2(rp, sx), gy = mul2(rp, sy), gz = mul2(rp, sz);                                                      \
+      acc[1] = add2(acc[1], gx); acc[2] = add2(acc[2], gy); acc[3] = add2(acc[3], gz);                                       \
+      acc[4] = fma2(gx, sx, acc[4]); acc[5] = fma2(gx, sy, acc[5]); acc[6] = fma2(gx, sz, acc[6]);                           \
+      acc[7] = fma2(gy, sy, acc[7]); acc[8] = fma2(gy, sz, acc[8]); acc[9] = fma2(gz, sz, acc[9]);                           \
     }                                                                                                                        \
-    const float fx = rp * ex, fy = rp * ey, fz = rp * ez; /* multiplication (not select): NaN must propagate */              \
-    acc[10] += fx; acc[11] += fy; acc[12] += fz;                                                                             \
-    const float wx = ax + sv.x, wy = ay + sv.y, wz = az + sv.z; /* R~ s in the world-oriented frame */                       \
-    acc[13] = fmaf(wy, fz, fmaf(-wz, fy, acc[13]));                                                                          \
-    acc[14] = fmaf(wz, fx, fmaf(-wx, fz, acc[14]));                                                                          \
-    acc[15] = fmaf(wx, fy, fmaf(-wy, fx, acc[15]));                                                                          \
+    const f2 fx = mul2(rp, ex), fy = mul2(rp, ey), fz = mul2(rp, ez); /* multiplication (not select): NaN must propagate */  \
+    acc[10] = add2(acc[10], fx); acc[11] = add2(acc[11], fy); acc[12] = add2(acc[12], fz);                                   \
+    const f2 wx = add2(ax, sx), wy = add2(ay, sy), wz = add2(az, sz); /* R~ s in the world-oriented frame */                 \
+    acc[13] = fma2(wy, fz, fma2(neg2(wz), fy, acc[13]));                                                                     \
+    acc[14] = fma2(wz, fx, fma2(neg2(wx), fz, acc[14]));                                                                     \
+    acc[15] = fma2(wx, fy, fma2(neg2(wy), fx, acc[15]));                                                                     \
   }
 
   for (int i = 0; i < n_my; i++) {
     const int s = i % S, k = i / S;
+    {
+      const int j = i + S - 1;  // the tile that takes over the stage of tile i-1
+      if (warp == i % NW && j < n_my) {
+        if (i > 0) mbar_wait(empty + j % S, (uint32_t)((j / S - 1) & 1));  // every warp has left tile i-1
+        tile_issue(j, cnt_pref);
+      }
+      if (warp == (i + 1) % NW && j + 1 < n_my) cnt_pref = tile_cnt(j + 1);
+    }
     mbar_wait(full + s, (uint32_t)(k & 1));
     const unsigned char *st = smem + (size_t)s * stage_bytes;
     const float4 *hdr = reinterpret_cast<const float4 *>(st + hdr_off);
@@ -568,8 +619,7 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
       rows_in_acc += __popc(m2 | m4 | ml);
       // ---- lists of one or two candidates (padded to 2: a one-candidate list carries a +inf sentinel that never wins).
       // Two rows per trip, written as one straight-line block so that the scheduler interleaves the two independent
-      // chains (4.5 warps per SM sub-partition do not hide the LDS / MUFU / FMA latencies of a single chain: 39 % of the
-      // issue slots went to `wait` and `short scoreboard` stalls); an odd last row is paired with a dead copy of itself.
+      // chains; an odd last row is paired with a dead copy of itself.
       while (m2) {
         const int r0 = __ffs(m2) - 1;
         m2 &= m2 - 1;
@@ -585,8 +635,9 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
           const float4 sv = sv0;
           SVN_QUERY
           SVN_DIST(c00, u) SVN_DIST(c01, v)
-          const bool p1 = vd < ud;  // strict '<': the first slot wins ties (mink.cuh:141); NaN compares false -> slot 0
-          const float best = p1 ? vd : ud, ex = p1 ? vx : ux, ey = p1 ? vy : uy, ez = p1 ? vz : uz;
+          // strict '<': the first slot wins ties (mink.cuh:141); NaN compares false -> slot 0
+          const bool p0 = lo(vd) < lo(ud), p1 = hi(vd) < hi(ud);
+          const f2 best = sel2(p0, p1, vd, ud), ex = sel2(p0, p1, vx, ux), ey = sel2(p0, p1, vy, uy), ez = sel2(p0, p1, vz, uz);
           SVN_ACCUM(true)
         }
         {
@@ -595,8 +646,8 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
           const float4 sv = sv1;
           SVN_QUERY
           SVN_DIST(c10, u) SVN_DIST(c11, v)
-          const bool p1 = vd < ud;
-          const float best = p1 ? vd : ud, ex = p1 ? vx : ux, ey = p1 ? vy : uy, ez = p1 ? vz : uz;
+          const bool p0 = lo(vd) < lo(ud), p1 = hi(vd) < hi(ud);
+          const f2 best = sel2(p0, p1, vd, ud), ex = sel2(p0, p1, vx, ux), ey = sel2(p0, p1, vy, uy), ez = sel2(p0, p1, vz, uz);
           SVN_ACCUM(two)
         }
       }
@@ -610,12 +661,12 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
         SVN_QUERY
         SVN_DIST(c0, u) SVN_DIST(c1, v) SVN_DIST(c2, w) SVN_DIST(c3, z)
         // tournament with strict '<' at every node: among equal distances the lowest slot wins, as slot-by-slot '<' would decide
-        const bool p1 = vd < ud, p3 = zd < wd;
-        const float m01 = p1 ? vd : ud, m23 = p3 ? zd : wd;
-        const float e01x = p1 ? vx : ux, e01y = p1 ? vy : uy, e01z = p1 ? vz : uz;
-        const float e23x = p3 ? zx : wx, e23y = p3 ? zy : wy, e23z = p3 ? zz : wz;
-        const bool p = m23 < m01;
-        const float best = p ? m23 : m01, ex = p ? e23x : e01x, ey = p ? e23y : e01y, ez = p ? e23z : e01z;
+        const bool p10 = lo(vd) < lo(ud), p11 = hi(vd) < hi(ud), p30 = lo(zd) < lo(wd), p31 = hi(zd) < hi(wd);
+        const f2 m01 = sel2(p10, p11, vd, ud), m23 = sel2(p30, p31, zd, wd);
+        const f2 e01x = sel2(p10, p11, vx, ux), e01y = sel2(p10, p11, vy, uy), e01z = sel2(p10, p11, vz, uz);
+        const f2 e23x = sel2(p30, p31, zx, wx), e23y = sel2(p30, p31, zy, wy), e23z = sel2(p30, p31, zz, wz);
+        const bool p0 = lo(m23) < lo(m01), p1 = hi(m23) < hi(m01);
+        const f2 best = sel2(p0, p1, m23, m01), ex = sel2(p0, p1, e23x, e01x), ey = sel2(p0, p1, e23y, e01y), ez = sel2(p0, p1, e23z, e01z);
         SVN_ACCUM(true)
       }
       // ---- longer lists: chunks of four, exact warp-voted early exit
@@ -627,45 +678,54 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
         const int n = __float_as_int(sv.w) >> 16;
         float4 c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
         SVN_QUERY
-        float best;
-        int bk = 0;  // first slot of the chunk that holds the running minimum
+        float best0, best1;
+        int bk0 = 0, bk1 = 0;  // first slot of the chunk that holds the running minimum (per particle)
         {
           SVN_DIST(c0, u) SVN_DIST(c1, v) SVN_DIST(c2, w) SVN_DIST(c3, z)
-          best = fminf(fminf(ud, vd), fminf(wd, zd));  // fminf drops NaN, like a strict '<' against +inf
-          if (!(best == best)) best = INFINITY;
+          const f2 m_ = min4_2(ud, vd, wd, zd);
+          best0 = lo(m_); best1 = hi(m_);
+          if (!(best0 == best0)) best0 = INFINITY;
+          if (!(best1 == best1)) best1 = INFINITY;
         }
-        // upper bound of |q| (distance of this particle's query from the initial-guess query q0_b)
-        const float qn = fmaf(sqrt_approx(fmaf(qz, qz, fmaf(qy, qy, qx * qx))), 1.00001f, 1e-7f);
+        // upper bound of |q| (distance of each particle's query from the initial-guess query q0_b)
+        const f2 qq = fma2(qz, qz, fma2(qy, qy, mul2(qx, qx)));
+        const f2 qn = fma2(pk(sqrt_approx(lo(qq)), sqrt_approx(hi(qq))), bc(1.00001f), bc(1e-7f));
         for (int k0 = 4; k0 < n; k0 += 4) {
           c0 = e[k0]; c1 = e[k0 + 1]; c2 = e[k0 + 2]; c3 = e[k0 + 3];
           // exact early exit: slots ascend in |c| (= c.w, a lower bound) and |q - c| >= |c| - |q|, so once
-          // (|c| - |q|)^2 > best no later slot can win or tie.  NaN anywhere compares false -> no exit.
-          const float tt = c0.w - qn;
-          const bool done = (tt > 0.f) && (tt * tt * 0.99999f > best);
+          // (|c| - |q|)^2 > best no later slot can win or tie.  NaN anywhere compares false -> no exit.  A particle whose
+          // partner (or warp) is not done yet keeps scanning: later slots cannot change its minimum.
+          const f2 tt = sub2(bc(c0.w), qn);
+          const f2 tb = mul2(mul2(tt, tt), bc(0.99999f));
+          const bool done = (lo(tt) > 0.f) && (lo(tb) > best0) && (hi(tt) > 0.f) && (hi(tb) > best1);
           if (UNI) { if (__all_sync(0xffffffffu, done)) break; }
           else { if (done) break; }
           // only the chunk minimum enters the running comparison; the slot inside the winning chunk is recovered afterwards
           SVN_DIST(c0, u) SVN_DIST(c1, v) SVN_DIST(c2, w) SVN_DIST(c3, z)
-          const float m_ = fminf(fminf(ud, vd), fminf(wd, zd));
-          if (m_ < best) { best = m_; bk = k0; }
+          const f2 m_ = min4_2(ud, vd, wd, zd);
+          if (lo(m_) < best0) { best0 = lo(m_); bk0 = k0; }
+          if (hi(m_) < best1) { best1 = hi(m_); bk1 = k0; }
         }
-        // first slot of the winning chunk whose distance IS the minimum: what slot-by-slot strict '<' would have kept
-        c0 = e[bk]; c1 = e[bk + 1]; c2 = e[bk + 2]; c3 = e[bk + 3];
-        SVN_DIST(c0, u) SVN_DIST(c1, v) SVN_DIST(c2, w) SVN_DIST(c3, z)
-        const bool h0 = ud == best, h1 = vd == best, h2 = wd == best;
-        float ex = h0 ? ux : h1 ? vx : h2 ? wx : zx, ey = h0 ? uy : h1 ? vy : h2 ? wy : zy, ez = h0 ? uz : h1 ? vz : h2 ? wz : zz;
-        if (best == INFINITY) { ex = ux; ey = uy; ez = uz; }  // nothing compared below +inf (NaN query): slot 0, as before
+        float ex0, ey0, ez0, ex1, ey1, ez1;
+        gn_recover(e, bk0, lo(qx), lo(qy), lo(qz), best0, ex0, ey0, ez0);
+        gn_recover(e, bk1, hi(qx), hi(qy), hi(qz), best1, ex1, ey1, ez1);
+        const f2 best = pk(best0, best1), ex = pk(ex0, ex1), ey = pk(ey0, ey1), ez = pk(ez0, ez1);
         SVN_ACCUM(true)
       }
       if (rows_in_acc >= GN_FLUSH_ROWS) {
 #pragma unroll
-        for (int j = 0; j < NACC; j++) { dacc[j] += (accum2_t)acc[j]; acc[j] = 0.f; }
+        for (int j = 0; j < NACC; j++) { dacc[j * GN_CONSUMERS] = add2(dacc[j * GN_CONSUMERS], acc[j]); acc[j] = 0; }
         rows_in_acc = 0;
         if (++flushes2 >= GN_FLUSH2 && active) {
-          // third level: fold into this thread's own fp64 partial slot (global, L2-resident) so that the fp32
+          // third level: fold into the two particles' own fp64 partial slots (global, L2-resident) so that the fp32
           // second level never carries more than GN_FLUSH2 * GN_FLUSH_ROWS rows, whatever the slice length
 #pragma unroll
-          for (int j = 0; j < NACC; j++) { out[j] = (wrote ? out[j] : 0.0) + (double)dacc[j]; dacc[j] = 0; }
+          for (int j = 0; j < NACC; j++) {
+            const f2 d = dacc[j * GN_CONSUMERS];
+            out[j] = (wrote ? out[j] : 0.0) + (double)lo(d);
+            if (active1) out[NACC + j] = (wrote ? out[NACC + j] : 0.0) + (double)hi(d);
+            dacc[j * GN_CONSUMERS] = 0;
+          }
           wrote = true;
           flushes2 = 0;
         }
@@ -679,7 +739,11 @@ __global__ void __launch_bounds__(GN_THREADS, SVN_GN_MINBLOCKS) k_gn(IterArgs a)
 #undef SVN_ACCUM
   if (active) {
 #pragma unroll
-    for (int j = 0; j < NACC; j++) out[j] = (wrote ? out[j] : 0.0) + ((double)dacc[j] + (double)acc[j]);
+    for (int j = 0; j < NACC; j++) {
+      const f2 d = dacc[j * GN_CONSUMERS];
+      out[j] = (wrote ? out[j] : 0.0) + ((double)lo(d) + (double)lo(acc[j]));
+      if (active1) out[NACC + j] = (wrote ? out[NACC + j] : 0.0) + ((double)hi(d) + (double)hi(acc[j]));
+    }
   }
 }
 
@@ -796,7 +860,7 @@ void init_iter_kernels() {
 // a k_gn CTA to retire (with the default carve-out the head chain finished ~26 us after k_gn, on the critical path)
 #define SVN_GN_ATTR(D, U, F)                                                                                  \
   do {                                                                                                        \
-    cudaFuncSetAttribute(k_gn<D, U, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);             \
+    cudaFuncSetAttribute(k_gn<D, U, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);             \
     cudaFuncSetAttribute(k_gn<D, U, F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
   } while (0)
   SVN_GN_ATTR(false, true, false); SVN_GN_ATTR(true, true, false); SVN_GN_ATTR(false, false, false); SVN_GN_ATTR(true, false, false);

@@ -108,6 +108,12 @@ int launch_finalize(const IterArgs &a, const PeerTable &pt, unsigned seq_h, cuda
 void init_iter_kernels();
 // bytes of one shared-memory stage of k_gn: TB pruned rows of K float4 + TB row headers + 3 row-class masks, 128-byte aligned
 __host__ __device__ inline size_t gn_stage_bytes(int TB, int K) { return ((size_t)TB * K * 16 + (size_t)TB * 16 + 16 + 127) & ~(size_t)127; }
+// k_gn launch shape: one CTA per SM of GN_CONSUMERS threads (each carries two particles; the warps take turns loading tiles).
+// Dynamic shared memory: [S] stages, 2*S mbarriers, then the second-level accumulators [NACC][GN_CONSUMERS] fp32 pairs.
+constexpr int GN_CONSUMERS = 512;
+constexpr int GN_THREADS = GN_CONSUMERS;
+__host__ __device__ inline size_t gn_dacc_offset(int TB, int K, int S) { return (gn_stage_bytes(TB, K) * S + 2 * (size_t)S * 8 + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t gn_smem_bytes(int TB, int K, int S) { return gn_dacc_offset(TB, K, S) + (size_t)NACC * GN_CONSUMERS * 8; }
 
 struct SteinArgs {
   int P, p_lo, P_l, I;
