@@ -73,8 +73,8 @@ typedef struct {
                                     iteration for svnicp_get_correspondences (parity tests)    */
   int32_t flags;                 /* SVNICP_FLAG_* bit mask, read once by svnicp_create (A/B measurements; 0 = the
                                     measured-best default path)                                  */
-  int32_t gn_stages;             /* TMA pipeline depth of the Gauss-Newton kernel (0 -> 3)      */
-  int32_t gn_smem_kb;            /* shared-memory budget of one Gauss-Newton CTA in KiB (0 -> 100) */
+  int32_t gn_stages;             /* bits 0-7: TMA ring depth of the Gauss-Newton kernel (0 -> 4); bits 8-15: refill lag in tiles (0 -> 2 when depth >= 4, else 1) */
+  int32_t gn_smem_kb;            /* shared-memory budget of the Gauss-Newton tile ring in KiB (0 -> 110, at most 150) */
 } svnicp_params;
 
 /* svnicp_params.flags (all default off; none changes a result beyond the documented summation-order effects) */

@@ -544,11 +544,11 @@ static int choose_shape(svnicp_handle h) {
   const int Kp = (h->K + 3) & ~3;
   h->Kp = Kp;
   int TB = 32;
-  int S = 3;
-  // one CTA of k_gn per SM: its tile ring may take ~100 KB next to the 64 KB of second-level accumulators, which leaves room
+  int S = 4;
+  // one CTA of k_gn per SM: its tile ring may take ~110 KB next to the 64 KB of second-level accumulators, which leaves room
   // for the small side-stream kernels (k_head_*, 33 KB) on the same SM
-  size_t budget = 100 * 1024;
-  if (h->prm.gn_stages > 1) S = h->prm.gn_stages;  // tuning knobs (svnicp_params extensions, bench sweeps)
+  size_t budget = 110 * 1024;
+  if ((h->prm.gn_stages & 255) > 1) S = h->prm.gn_stages & 255;  // tuning knobs (svnicp_params extensions, bench sweeps)
   if (h->prm.gn_smem_kb > 0) budget = (size_t)(h->prm.gn_smem_kb < 150 ? h->prm.gn_smem_kb : 150) * 1024;
   const int consumers = GN_CONSUMERS;  // every consumer thread of k_gn carries two particles (packed fp32 pairs)
   while (TB > 4 && gn_stage_bytes(TB, Kp) * S > budget) TB >>= 1;
@@ -784,6 +784,7 @@ static int align_begin(svnicp_handle h, AlignState &S) {
   ia.sp = h->sp.p; ia.cand = h->cand.p; ia.clist = h->clist.p; ia.hdr = h->hdr.p;
   ia.R = h->R.p; ia.t = h->t.p; ia.xf = h->xf.p; ia.dnorm = h->dnorm.p; ia.part = h->part.p; ia.rec = h->rec; ia.rec_stride = h->rec_stride; ia.ctrl = h->ctrl.p;
   ia.TB = h->TB; ia.stages = h->stages; ia.n_slices = h->n_slices; ia.n_pgroups = h->n_pgroups; ia.PG = h->PG; ia.RG = h->RG;
+  ia.gn_lag = (h->prm.gn_stages >> 8) ? (h->prm.gn_stages >> 8) : ((h->stages >= 4) ? 2 : 1);
   ia.gn_smem = h->gn_smem; ia.sm_count = h->sm_count; ia.svn_full_grad = h->prm.SVN_full_grad;
   ia.first_order = svgd ? 1 : 0;
   ia.dbg_idx = h->prm.debug_corr ? h->dbg_idx.p : nullptr;

@@ -501,8 +501,10 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
 
   // ---------------- tile loads: 1-D TMA bulk copies of the pruned lists + the row-class masks ----------------
   // There is no producer warp (a 17th warp would round the CTA's register allocation up to 20 warps: 96 registers per
-  // thread).  The warps take turns instead: at tile i, warp i % 16 refills the stage that tile i-1 has just left with tile
-  // i+S-1; it fetched that tile's list lengths one tile earlier, so the only wait it adds is for the slowest warp's tile i-1.
+  // thread).  The warps take turns instead: at tile i, warp i % 16 refills the stage that tile i-LAG left with tile i+AHEAD
+  // (AHEAD = S - LAG tiles in flight ahead of the slowest warp).  With S >= 4 the stage it refills was left TWO tiles ago, so
+  // the wait for the slowest warp is normally over before it starts (with LAG = 1 it was 9 % of all stall samples; measured
+  // 22.4 -> 21.6 ms per scan at configs[1]); the tile's list lengths were fetched one tile earlier.
   constexpr int NW = GN_CONSUMERS / 32;
   auto tile_cnt = [&](int j) -> int {  // padded list length of row `lane` of this CTA's j-th tile
     return (lane < TB) ? (__float_as_int(__ldg(&a.hdr[(size_t)(slice + j * n_slices) * TB + lane].w)) >> 16) : 0;
@@ -526,9 +528,10 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
     if (lane < TB && cnt > 0) bulk_g2s(st + (size_t)lane * Kp * 16, a.clist + (size_t)(row0 + lane) * Kp, (uint32_t)bytes, full + s);
     if (lane == 0) bulk_g2s(st + hdr_off, a.hdr + row0, (uint32_t)(TB * 16), full + s);
   };
-  for (int j = 0; j < S - 1 && j < n_my; j++)
+  const int LAG = (a.gn_lag < S) ? a.gn_lag : 1, AHEAD = S - LAG;
+  for (int j = 0; j < AHEAD && j < n_my; j++)
     if (warp == j % NW) tile_issue(j, tile_cnt(j));
-  int cnt_pref = (warp == 0 && S - 1 < n_my) ? tile_cnt(S - 1) : 0;
+  int cnt_pref = (warp == 0 && AHEAD < n_my) ? tile_cnt(AHEAD) : 0;
 
   // ---------------- consumers: one thread = two particles (x RG row groups) ----------------
   const int PG = a.PG, RG = a.RG;  // PG = consumer threads (particle PAIRS) per row group
@@ -602,9 +605,9 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
   for (int i = 0; i < n_my; i++) {
     const int s = i % S, k = i / S;
     {
-      const int j = i + S - 1;  // the tile that takes over the stage of tile i-1
+      const int j = i + AHEAD;  // the tile that takes over the stage of tile i-LAG
       if (warp == i % NW && j < n_my) {
-        if (i > 0) mbar_wait(empty + j % S, (uint32_t)((j / S - 1) & 1));  // every warp has left tile i-1
+        if (j >= S) mbar_wait(empty + j % S, (uint32_t)((j / S - 1) & 1));  // every warp has left tile j-S = i-LAG
         tile_issue(j, cnt_pref);
       }
       if (warp == (i + 1) % NW && j + 1 < n_my) cnt_pref = tile_cnt(j + 1);

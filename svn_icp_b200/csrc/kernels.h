@@ -59,6 +59,7 @@ struct IterArgs {
   Ctrl *ctrl;
   // launch shape of the Gauss-Newton kernel
   int TB, stages, n_slices, n_pgroups, PG, RG;
+  int gn_lag;          // k_gn: a tile's stage is refilled gn_lag tiles after it was consumed (1 or 2)
   size_t gn_smem;
   int sm_count;
   int svn_full_grad;
