@@ -427,19 +427,20 @@ def main():
     ph_ff = icp_ff.get_phase_times()
     icp_ff.close()
     t_filter = ph_ff["filter_ms"] / max(ph_ff["iterations"], 1) * 1e-3
-    fp32_peak_results = 148 * 128 * sm_max * 1e6  # FP32 results/s: 128 lanes per SM (FFMA2 issues at half rate: scripts/micro/ffma2_bench.cu)
+    fp32_peak_results = 148 * 128 * sm_max * 1e6  # FP32 results/s: 128 lanes per SM, as FFMA or FFMA2 (scripts/ubench/ffma2.cu)
     roofline = dict(bound="hbm", kernel="k_filter + k_gn (correspondence + Gauss-Newton reduction pass, per iteration)",
                     achieved=b_alg / t_pass / 1e9, peak=hbm_peak, unit="GB/s", frac=b_alg / t_pass / 1e9 / hbm_peak, traffic=None,
                     peak_source=peak_src, algorithmic_bytes_per_launch=b_alg, ms_per_launch=t_pass * 1e3,
-                    note="the pass is FP32-issue bound for P >~ 20 (every loaded byte is reused by all particles: 0.57*P flop/B); the "
+                    note="the pass is FP32 bound for P >~ 20 (every loaded byte is reused by all particles: 0.57*P flop/B): k_gn "
+                         "carries two particles per thread in packed fp32 (FFMA2), FMA pipe 62-67 % busy (ncu, profiles/); the "
                          "HBM-bound kernel of the path is k_filter alone (filter_only)",
                     filter_only=dict(achieved=16.0 * n_s * (1 + K) / t_filter / 1e9, frac=16.0 * n_s * (1 + K) / t_filter / 1e9 / hbm_peak,
                                      ms_per_launch=t_filter * 1e3,
                                      note="k_filter streaming the K-slot table every iteration (SVNICP_FLAG_FILTER_FULL scan)"),
-                    gn_issue=dict(ms_per_launch=ph["gn_ms"] / iters, pairs_per_launch=float(P_g) * n_s,
-                                  ns_per_pair_per_sm_lane=ph["gn_ms"] / iters * 1e-3 * fp32_peak_results / (float(P_g) * n_s),
-                                  note="k_gn time expressed as FP32 issue slots per (particle, point) pair at 128 lanes/SM x sm_max; the executed "
-                                       "FP32 instruction count per pair is in profiles/ (ncu)"))
+                    gn_fp32=dict(ms_per_launch=ph["gn_ms"] / iters, pairs_per_launch=float(P_g) * n_s,
+                                 fma_lane_cycles_per_pair=ph["gn_ms"] / iters * 1e-3 * fp32_peak_results / (float(P_g) * n_s),
+                                 note="k_gn time expressed as FMA-pipe lane-cycles (128 per SM and clock at sm_max) per (particle, point) "
+                                      "pair, averaged over the scan; the executed packed-instruction counts are in profiles/ (ncu)"))
     # dram__bytes_{read,write}.sum per launch from the committed ncu --set full captures (profiles/), if present
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))

@@ -188,7 +188,7 @@ def run(args, rank, world, local_rank):
                                       algorithmic_bytes_per_launch=b_setup, ms_per_launch=ph["setup_ms"],
                                       note="k_knn is a latency-bound ring search (one dependent chain per query warp), not a streaming pass",
                                       iteration_pass=dict(kernel="k_filter + k_gn", achieved=b_iter / t_pass / 1e9, frac=b_iter / t_pass / 1e9 / hbm_peak,
-                                                          ms_per_launch=t_pass * 1e3, note="FP32-issue bound at 16384 particles (0.57*P flop/B)"),
+                                                          ms_per_launch=t_pass * 1e3, note="FP32 (FMA pipe) bound at 16384 particles (0.57*P flop/B)"),
                                       stein_phase=dict(ms_per_iteration=ph["stein_ms"] / iters, pairs=float(P_g) * P,
                                                        note="k_tail: P_g x P kernel-weighted 6x6 Hessian sums in fp64; the reference would "
                                                             "materialise [P,P,6,6] = 77 GB here (SVNICP.cpp:236-237)")),
