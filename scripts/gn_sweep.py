@@ -5,7 +5,7 @@ import svn_icp_b200 as sv
 from svn_icp_b200 import synth
 pb = synth.make_problem_saturated(1000, sensor="64")
 rng = np.random.default_rng(5)
-for P, stages, kb in [(1000, 0, 0), (1000, 256 + 4, 0), (500, 0, 0), (500, 256 + 4, 0), (125, 0, 0), (125, 256 + 4, 0), (125, 256 + 5, 135), (125, 512 + 5, 135), (1000, 512 + 5, 135), (30, 256 + 4, 0)]:
+for P, stages, kb in [(1000, 0, 0), (500, 0, 0), (250, 0, 0), (125, 0, 0), (100, 0, 0), (30, 0, 0)]:
     init = synth.init_particles(P, rng)
     icp = sv.SVNICP(sv.SteinICPParam(iterations=30, KNN_count=100, max_dist=3.0, lr=1.0, gn_stages=stages, gn_smem_kb=kb), init)
     icp.set_profiling(True)

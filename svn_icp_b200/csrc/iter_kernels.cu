@@ -622,38 +622,36 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
       rows_in_acc += __popc(m2 | m4 | ml);
       // ---- lists of one or two candidates (padded to 2: a one-candidate list carries a +inf sentinel that never wins).
       // Two rows per trip, written as one straight-line block so that the scheduler interleaves the two independent
-      // chains; an odd last row is paired with a dead copy of itself.
-      while (m2) {
+      // chains; an odd last row gets a single-row body (pairing it with a dead copy of itself wasted a row's worth of
+      // arithmetic: 5 % of this class at 16 rows per thread and tile, 40 % at 2 rows -- the sharded slices).
+#define SVN_ROW2(SV, CA, CB)                                                                                            \
+  {                                                                                                                     \
+    const float4 sv = (SV);                                                                                             \
+    SVN_QUERY                                                                                                           \
+    SVN_DIST(CA, u) SVN_DIST(CB, v)                                                                                     \
+    /* strict '<': the first slot wins ties (mink.cuh:141); NaN compares false -> slot 0 */                             \
+    const bool p0 = lo(vd) < lo(ud), p1 = hi(vd) < hi(ud);                                                              \
+    const f2 best = sel2(p0, p1, vd, ud), ex = sel2(p0, p1, vx, ux), ey = sel2(p0, p1, vy, uy), ez = sel2(p0, p1, vz, uz); \
+    SVN_ACCUM(true)                                                                                                     \
+  }
+      while (m2 & (m2 - 1)) {  // at least two rows left
         const int r0 = __ffs(m2) - 1;
         m2 &= m2 - 1;
-        const bool two = m2 != 0;
-        const int r1 = two ? __ffs(m2) - 1 : r0;
+        const int r1 = __ffs(m2) - 1;
         m2 &= m2 - 1;
         const float4 sv0 = hdr[r0], sv1 = hdr[r1];
         const float4 *e0 = lists + r0 * Kp, *e1 = lists + r1 * Kp;
         const float4 c00 = e0[0], c01 = e0[1], c10 = e1[0], c11 = e1[1];
-        {
-          const int r = r0;
-          (void)r;
-          const float4 sv = sv0;
-          SVN_QUERY
-          SVN_DIST(c00, u) SVN_DIST(c01, v)
-          // strict '<': the first slot wins ties (mink.cuh:141); NaN compares false -> slot 0
-          const bool p0 = lo(vd) < lo(ud), p1 = hi(vd) < hi(ud);
-          const f2 best = sel2(p0, p1, vd, ud), ex = sel2(p0, p1, vx, ux), ey = sel2(p0, p1, vy, uy), ez = sel2(p0, p1, vz, uz);
-          SVN_ACCUM(true)
-        }
-        {
-          const int r = r1;
-          (void)r;
-          const float4 sv = sv1;
-          SVN_QUERY
-          SVN_DIST(c10, u) SVN_DIST(c11, v)
-          const bool p0 = lo(vd) < lo(ud), p1 = hi(vd) < hi(ud);
-          const f2 best = sel2(p0, p1, vd, ud), ex = sel2(p0, p1, vx, ux), ey = sel2(p0, p1, vy, uy), ez = sel2(p0, p1, vz, uz);
-          SVN_ACCUM(two)
-        }
+        { const int r = r0; (void)r; SVN_ROW2(sv0, c00, c01) }
+        { const int r = r1; (void)r; SVN_ROW2(sv1, c10, c11) }
       }
+      if (m2) {
+        const int r = __ffs(m2) - 1;
+        const float4 *e0 = lists + r * Kp;
+        const float4 sv0 = hdr[r], c00 = e0[0], c01 = e0[1];
+        SVN_ROW2(sv0, c00, c01)
+      }
+#undef SVN_ROW2
       // ---- three or four candidates (padded to 4)
       while (m4) {
         const int r = __ffs(m4) - 1;
