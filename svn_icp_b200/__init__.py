@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsvnicp_b200.so")
+# SVNICP_B200_LIB: load another build of the same library (tests use it for the -DSVN_DEBUG_BOUNDS build); never a fallback
+LIB_PATH = os.environ.get("SVNICP_B200_LIB") or os.path.join(_HERE, "lib", "libsvnicp_b200.so")
 
 ALIGN_SUCCESS = 1  # SteinICPState, SVGDICP.h:59-62
 NO_OPTIMIZER = 2

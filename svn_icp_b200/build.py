@@ -26,9 +26,13 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False) -> str:
+    """debug_bounds=True builds lib/libsvnicp_b200_dbg.so with -DSVN_DEBUG_BOUNDS (device-side bounds checks, see common.cuh);
+    tests load it through SVNICP_B200_LIB."""
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj_dbg" if debug_bounds else "obj")
+    lib = LIB.replace(".so", "_dbg.so") if debug_bounds else LIB
+    flags = FLAGS + (["-DSVN_DEBUG_BOUNDS"] if debug_bounds else [])
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs, procs = [], []
@@ -37,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for name, p in procs:
@@ -47,11 +51,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl", "-ccbin", "/usr/bin/g++"]
+    if force or procs or _stale(lib, objs):
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-ldl", "-ccbin", "/usr/bin/g++"]
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug_bounds="--debug-bounds" in sys.argv))

@@ -973,6 +973,7 @@ static int align_finish(svnicp_handle h, AlignState &S) {
   }
   CU(cudaStreamSynchronize(st));
   h->iters_done = h->h_ctrl->iters_done;
+  if (h->h_ctrl->error >= 100) return fail(h, SVNICP_ERR_CUDA, "device bounds check %d failed (SVN_DEBUG_BOUNDS build)", h->h_ctrl->error - 100);
   if (h->h_ctrl->error) return fail(h, SVNICP_ERR_CUDA, "peer exchange timed out: another rank did not publish its records (rank %d of %d)", h->rank, h->n_ranks);
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->ms_setup = ms;

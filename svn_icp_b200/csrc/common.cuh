@@ -40,7 +40,8 @@ struct Ctrl {
   int stop;         // 1 once the early stop fired (all later kernels return immediately)
   int iter;         // iterations whose pose update has been applied
   int iters_done;   // == iter at the moment of the stop
-  int error;        // 1: a wait on a peer's flag timed out (sharded handles); the host reports it after the scan
+  int error;        // 1: a wait on a peer's flag timed out (sharded handles); >= 100: a device-side bounds check of the
+                    // -DSVN_DEBUG_BOUNDS build failed (code = 100 + check id); the host reports it after the scan
   unsigned fin_ticket, tail_ticket;  // CTAs of k_finalize / k_tail that have finished (the last one publishes)
   unsigned pad1, pad2;
   double bandwidth;  // h of the last Stein step
@@ -69,6 +70,15 @@ struct Ctrl {
 constexpr int MAX_RANKS = 8;
 constexpr int FLAG_H = 0;  // "b, H (g) of iteration seq are in your buffer"   (k_finalize -> k_tail)
 constexpr int FLAG_X = 1;  // "x, |delta| after update seq are in your buffer" (k_tail -> k_head)
+// Device-side bounds checks of the debug build (build.py --debug-bounds -> libsvnicp_b200_dbg.so; compute-sanitizer is not
+// available on the target pool).  A failed check records 100 + id in ctrl->error (first failure wins) and the access is skipped
+// or clamped by the caller; svnicp_align then fails with the id in its message.  The release build compiles them away.
+#ifdef SVN_DEBUG_BOUNDS
+#define SVN_CHECK(ctrl, cond, id) do { if (!(cond)) atomicCAS(&(ctrl)->error, 0, 100 + (id)); } while (0)
+#else
+#define SVN_CHECK(ctrl, cond, id) do { } while (0)
+#endif
+
 struct PeerTable {
   int n_ranks, rank;
   double *rec[MAX_RANKS];     // record block of rank r as mapped HERE (rec[rank] = the local block)

@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(256, 4) k_filter(IterArgs a) {  // 64 register
     }
     // pad to a multiple of 4 with sentinels that can never win (d = inf, strict '<') so k_gn scans in chunks of 4
     const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);  // k_gn scans 2, then chunks of 4
+    SVN_CHECK(a.ctrl, padded <= a.Kp && b < a.n_pad, 10);
     if (lane < padded - base) out[base + lane] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
     if (lane == 0) {
       a.hdr[b] = make_float4(s.x, s.y, s.z, __int_as_float((padded << 16) | base));  // row header of k_gn: source point + list length
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(256, 4) k_filter_reuse(IterArgs a) {
         if (!(d2 > thr)) out[base++] = e;
       }
       const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);
+      SVN_CHECK(a.ctrl, padded <= a.Kp && b < a.n_pad, 11);
       for (int k = base; k < padded; k++) out[k] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
       a.hdr[b] = make_float4(r.sx, r.sy, r.sz, __int_as_float((padded << 16) | base));
       a.cbase[b] = base;
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(256, 4) k_filter_reuse(IterArgs a) {
         base += __popc(m);
       }
       const int padded = (base <= 2) ? 2 : ((base + 3) & ~3);
+      SVN_CHECK(a.ctrl, padded <= a.Kp && bb < a.n_pad, 12);
       if (lane < padded - base) out[base + lane] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
       if (lane == 0) {
         a.hdr[bb] = make_float4(sx, sy, sz, __int_as_float((padded << 16) | base));
@@ -515,6 +518,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
     unsigned char *st = smem + (size_t)s * stage_bytes;
     const unsigned m2 = __ballot_sync(0xffffffffu, cnt == 2), m4 = __ballot_sync(0xffffffffu, cnt == 4), ml = __ballot_sync(0xffffffffu, cnt > 4);
     const int bytes = cnt * 16;
+    SVN_CHECK(a.ctrl, cnt >= 0 && cnt <= Kp && row0 + TB <= a.n_pad, 1);
     int total = bytes;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
@@ -553,6 +557,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
   int rows_in_acc = 0, flushes2 = 0;
   bool wrote = false;
   double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + (active ? l0 : 0)) * NACC;  // particle l1: out + NACC
+  SVN_CHECK(a.ctrl, PG * RG == GN_CONSUMERS && (int)gridDim.x == a.n_slices && gn_smem_bytes(TB, Kp, S) <= 227 * 1024, 4);
   // rows of a tile this thread owns: r = rg, rg + RG, ... (RG is a power of two dividing TB or larger than it)
   unsigned rgmask = 0;
   for (int r = rg; r < TB; r += RG) rgmask |= 1u << r;
@@ -677,6 +682,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
         const float4 sv = hdr[r];
         const float4 *e = lists + r * Kp;
         const int n = __float_as_int(sv.w) >> 16;
+        SVN_CHECK(a.ctrl, n > 4 && n <= Kp && (n & 3) == 0 && r < TB, 2);
         float4 c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
         SVN_QUERY
         float best0, best1;
@@ -707,6 +713,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
           if (lo(m_) < best0) { best0 = lo(m_); bk0 = k0; }
           if (hi(m_) < best1) { best1 = hi(m_); bk1 = k0; }
         }
+        SVN_CHECK(a.ctrl, bk0 >= 0 && bk0 + 3 < n && bk1 >= 0 && bk1 + 3 < n, 3);
         float ex0, ey0, ez0, ex1, ey1, ez1;
         gn_recover(e, bk0, lo(qx), lo(qy), lo(qz), best0, ex0, ey0, ez0);
         gn_recover(e, bk1, hi(qx), hi(qy), hi(qz), best1, ex1, ey1, ez1);
@@ -762,6 +769,7 @@ __global__ void __launch_bounds__(128) k_finalize(IterArgs a, PeerTable pt, unsi
   double v[NACC];
   gn_sum_partials(a, l, v);
   const int p = a.p_lo + l;
+  SVN_CHECK(ctl, l < a.P_l && p < a.P && (size_t)(p + 1) * REC <= a.rec_stride, 20);
   const size_t buf_off = (size_t)(ctl->iter & 1) * a.rec_stride;
   if (threadIdx.x == 0) {
     const double *R0 = a.sc.R0;

@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(SteinArgs a, IterArgs ia
     const int l = blockIdx.x * NI + ii;
     const bool active = ii < NI && l < a.P_l;
     const int i = a.p_lo + (active ? l : 0);
+    SVN_CHECK(c, i < P && (size_t)n_tiles * TJ * REC <= a.rec_stride && NI * JQ == TL_WARPS, 30);
     double xi[6];
 #pragma unroll
     for (int d = 0; d < 6; d++) xi[d] = __ldcg(rec + (size_t)i * REC + REC_X + d);
