@@ -84,6 +84,9 @@ typedef struct {
 #define SVNICP_FLAG_DEBUG_SYNC 32       /* synchronise after every launch group of an iteration and log it to stderr      */
 #define SVNICP_FLAG_WATCHDOG 64         /* svnicp_align polls the streams instead of blocking and reports a scan that does not
                                            finish within 8 s (which stream, the device-side iteration state) as an error     */
+#define SVNICP_FLAG_NO_GRAPH 128        /* never replay iterations as CUDA graphs (A/B measurements)                      */
+#define SVNICP_FLAG_FORCE_GRAPH 256     /* replay iterations >= 1 as CUDA graphs whatever the problem size (default: only
+                                           unsharded SVN-ICP handles without early stop and N_s * P <= 1e7: host-enqueue bound) */
 #define SVNICP_FLAG_REUSE_STATS 16      /* svnicp_get_prune_stats reports the fraction of rows served by list reuse    */
 
 /* Fill with the defaults of SteinICPParam (SVGDICP.h:41-57). */

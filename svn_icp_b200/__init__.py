@@ -46,6 +46,8 @@ FLAG_NCCL_GATHER = 8
 FLAG_REUSE_STATS = 16
 FLAG_DEBUG_SYNC = 32
 FLAG_WATCHDOG = 64
+FLAG_NO_GRAPH = 128
+FLAG_FORCE_GRAPH = 256
 
 
 @dataclasses.dataclass

@@ -541,9 +541,9 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
   const int PG = a.PG, RG = a.RG;  // PG = consumer threads (particle PAIRS) per row group
   const int pl = tid % PG, rg = tid / PG;
   const int l0 = 2 * (blockIdx.y * PG + pl), l1 = l0 + 1;  // local particle indices
-  const bool active = l0 < a.P_l, active1 = l1 < a.P_l;
+  const bool active0 = l0 < a.P_l, active1 = l1 < a.P_l;
   f2 A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, A6 = 0, A7 = 0, A8 = 0, t0 = 0, t1 = 0, t2 = 0;
-  if (active) {
+  if (active0) {
     const float *xa = a.xf + (size_t)l0 * 12, *xb = a.xf + (size_t)(active1 ? l1 : l0) * 12;  // an odd tail pairs with itself
     A0 = pk(xa[0], xb[0]); A1 = pk(xa[1], xb[1]); A2 = pk(xa[2], xb[2]); A3 = pk(xa[3], xb[3]); A4 = pk(xa[4], xb[4]);
     A5 = pk(xa[5], xb[5]); A6 = pk(xa[6], xb[6]); A7 = pk(xa[7], xb[7]); A8 = pk(xa[8], xb[8]);
@@ -556,7 +556,9 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
   for (int i = 0; i < NACC; i++) { acc[i] = 0; dacc[i * GN_CONSUMERS] = 0; }
   int rows_in_acc = 0, flushes2 = 0;
   bool wrote = false;
-  double *out = a.part + (((size_t)slice * RG + rg) * a.P_l + (active ? l0 : 0)) * NACC;  // particle l1: out + NACC
+  const int RGe = RG < TB ? RG : TB;  // row groups that own rows (rg >= TB: none, they neither accumulate nor write partials)
+  const bool active = active0 && rg < RGe;
+  double *out = a.part + (((size_t)slice * RGe + (rg < RGe ? rg : 0)) * a.P_l + (active ? l0 : 0)) * NACC;  // particle l1: out + NACC
   SVN_CHECK(a.ctrl, PG * RG == GN_CONSUMERS && (int)gridDim.x == a.n_slices && gn_smem_bytes(TB, Kp, S) <= 227 * 1024, 4);
   // rows of a tile this thread owns: r = rg, rg + RG, ... (RG is a power of two dividing TB or larger than it)
   unsigned rgmask = 0;
@@ -760,7 +762,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) k_gn(IterArgs a) {  // 16 warps
 // go into the record buffer of this iteration's parity on EVERY rank (peer stores over NVLink when sharded); the CTA that
 // finishes last publishes the sequence number in the peers' flag blocks (k_tail waits for it).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_finalize(IterArgs a, PeerTable pt, unsigned seq_h) {
+__global__ void __launch_bounds__(FIN_WARPS * 32) k_finalize(IterArgs a, PeerTable pt, unsigned seq_h) {
   Ctrl *ctl = a.ctrl;
   if (ctl->stop) return;
   __shared__ double s_out[REC];
@@ -925,7 +927,7 @@ int launch_gn(const IterArgs &a, cudaStream_t st) {
 }
 
 int launch_finalize(const IterArgs &a, const PeerTable &pt, unsigned seq_h, cudaStream_t st) {
-  if (a.P_l > 0) k_finalize<<<a.P_l, FIN_WARPS * 32, 0, st>>>(a, pt, seq_h);
+  if (a.P_l > 0) k_finalize<<<a.P_l, fin_threads(a), 0, st>>>(a, pt, seq_h);
   return 1;
 }
 

@@ -70,17 +70,20 @@ struct IterArgs {
 };
 #ifdef __CUDACC__
 // Fixed-order fp64 sum of the Gauss-Newton partial rows of local particle l (k_finalize, k_finalize_first): one CTA of
-// FIN_WARPS warps per particle.  Lane (j = lane & 15, half = lane >> 4) of warp w sums partial rows half + 2 (w + FIN_WARPS k)
-// of sum j over four independent chains, the odd half joins the even one, then the warps are added in ascending order.
+// nw = blockDim.x / 32 warps per particle (fin_threads: 4 warps, 8 when there are many partial rows -- small particle counts,
+// where k_gn runs many row groups).  Lane (j = lane & 15, half = lane >> 4) of warp w sums partial rows half + 2 (w + nw k) of sum
+// j over four independent chains, the odd half joins the even one, then the warps are added in ascending order.
 // The order depends only on the number of partial rows, never on timing.  Result: v[0..NACC) valid in EVERY thread of the CTA.
-constexpr int FIN_WARPS = 4;
+constexpr int FIN_WARPS = 8;  // at most
+__host__ __device__ inline int fin_rows(const IterArgs &a) { return a.n_slices * (a.RG < a.TB ? a.RG : a.TB); }  // row groups beyond TB own no rows
+inline int fin_threads(const IterArgs &a) { return fin_rows(a) > 512 ? FIN_WARPS * 32 : 128; }
 __device__ __forceinline__ void gn_sum_partials(const IterArgs &a, int l, double v[NACC]) {
   __shared__ double s_fin[FIN_WARPS][NACC];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int nrows = a.n_slices * a.RG;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nrows = fin_rows(a);
   const int j16 = lane & 15, half = lane >> 4;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  const int step = 2 * FIN_WARPS;
+  const int step = 2 * nw;
   int r = half + 2 * w;
   for (; r + 3 * step < nrows; r += 4 * step) {
     s0 += a.part[((size_t)r * a.P_l + l) * NACC + j16];
@@ -96,8 +99,7 @@ __device__ __forceinline__ void gn_sum_partials(const IterArgs &a, int l, double
 #pragma unroll
   for (int j = 0; j < NACC; j++) {
     double t = s_fin[0][j];
-#pragma unroll
-    for (int ww = 1; ww < FIN_WARPS; ww++) t += s_fin[ww][j];
+    for (int ww = 1; ww < nw; ww++) t += s_fin[ww][j];
     v[j] = t;
   }
 }

@@ -48,7 +48,7 @@ __global__ void k_svgd_init(SvgdArgs s, const double *init_pose, double *R, doub
 // partial sums -> sgd_grad of one particle (one warp each), into the gathered record:
 //   rec.x = the particle's KERNEL position (pose_particles_: `prev` in iteration 0, the parameters afterwards)
 //   rec.b = sgd_gradient * gradient_scaling_factor_   (:454)
-__global__ void __launch_bounds__(128) k_finalize_first(IterArgs a, SvgdArgs s) {
+__global__ void __launch_bounds__(FIN_WARPS * 32) k_finalize_first(IterArgs a, SvgdArgs s) {
   if (a.ctrl->stop) return;
   const int l = blockIdx.x;  // one CTA (FIN_WARPS warps) per local particle, same fixed order as k_finalize
   double v[NACC];
@@ -253,7 +253,7 @@ int launch_svgd_init(const SvgdArgs &s, const double *init_pose_dev, double *R, 
   return 1;
 }
 int launch_finalize_first(const IterArgs &a, const SvgdArgs &s, cudaStream_t st) {
-  if (a.P_l > 0) k_finalize_first<<<a.P_l, FIN_WARPS * 32, 0, st>>>(a, s);
+  if (a.P_l > 0) k_finalize_first<<<a.P_l, fin_threads(a), 0, st>>>(a, s);
   return 1;
 }
 int launch_svgd_rec(double *rec, const double *src6, const double *dnorm, int lo, int n, int dn_off, cudaStream_t st) {

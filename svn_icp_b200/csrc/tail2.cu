@@ -344,24 +344,21 @@ __global__ void __launch_bounds__(HD_THREADS, 8) k_head_radix(SteinArgs a, int s
 }
 
 // Small particle sets (P <= HD_SMALL_P): the whole chain in ONE CTA -- one launch instead of eight, no inter-CTA hand-over.
-// Same steps, same helpers, same values.  x is staged in shared memory; the histogram of a pass goes through the global
-// scratch only because hd_select reads it from there.
-constexpr int HD_SMALL_P = 64;  // one CTA of 128 threads: 2016 pairs, ~15 us; beyond that the chain over many CTAs is faster (measured at 100 and 256)
+// Same decision, same history row, same pair distances (hd_sweep); the median comes from a sort of all pairs in shared memory.
+constexpr int HD_SMALL_P = 64;  // one CTA of 128 threads: 2016 pairs; beyond that the chain over many CTAs is faster (measured at 100 and 256)
 __global__ void __launch_bounds__(HD_THREADS, 8) k_head_small(SteinArgs a, PeerTable pt, unsigned seq_x, int epilogue) {
   Ctrl *c = a.ctrl;
   if (c->stop) return;
-  __shared__ __align__(16) unsigned s_hist[MED_BINS];      // histogram / collected values (32 KB)
-  __shared__ __align__(16) double s_x[6 * HD_SMALL_P];     // 12 KB
+  __shared__ __align__(16) unsigned s_hist[MED_BINS];      // the pair distances as 64-bit keys (32 KB = 4096 slots)
+  __shared__ __align__(16) double s_x[6 * HD_SMALL_P];     // 3 KB
   __shared__ double s_red[HD_WARPS];
-  __shared__ unsigned long long s_warp[32], s_res[2], s_val;
   __shared__ unsigned s_cursor;
-  __shared__ int s_stop, s_found;
+  __shared__ int s_stop;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = a.P;
   if (seq_x) peer_wait(pt, FLAG_X, seq_x, c);
   const int it = c->iter;
   const double *rec = a.rec + (size_t)(it & 1) * a.rec_stride;
-  const double med_guess = c->bandwidth * log((double)(P + 1));
   double s = 0.0;
   for (int p = tid; p < P; p += blockDim.x) s += __ldcg(rec + (size_t)p * REC + REC_DNORM);
   s = warp_sum(s);
@@ -385,45 +382,37 @@ __global__ void __launch_bounds__(HD_THREADS, 8) k_head_small(SteinArgs a, PeerT
   }
   if (epilogue || P < 2) return;
   __syncthreads();
-  const unsigned long long rank0 = ((unsigned long long)P * (unsigned long long)P - 1ull) / 2ull;  // lower median
-  bool have = false;
-  double median = 0.0;
-  if (P >= 8 && it > 0 && med_guess > 0.0 && med_guess < INFINITY) {
-    const HdWindow w = hd_window(med_guess);
-    for (int i = tid; i < MED_BINS; i += blockDim.x) s_hist[i] = 0u;
-    __syncthreads();
-    hd_fast_hist(s_x, P, w, s_hist, 0, 1);
-    __syncthreads();
-    for (int i = tid; i < MED_BINS; i += blockDim.x) a.hist[i] = s_hist[i];
-    __syncthreads();
-    unsigned long long tbin = 0ull, trank = 0ull;
-    hd_select(a.hist, 0ull, rank0, MED_BINS, 13, &tbin, &trank, s_warp, s_res);
-    if (tbin != 0ull && tbin != (unsigned long long)(MED_BINS - 1)) {
-      if (tid == 0) s_cursor = 0u;
+  // P <= 64: at most 2016 unordered pairs.  Sort them (bitonic network in shared memory; keys = bit patterns: non-negative
+  // doubles order like their bits and NaN sorts last -- exactly the order the radix select of the multi-CTA chain uses) and
+  // read the order statistic off: the P x P matrix holds P exact zeros and every pair twice.  ~2 us at P = 30 (the histogram
+  // passes this replaces took 43 us on average and sat on the critical path of small scans).
+  unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_hist);  // MED_BINS / 2 = 4096 slots
+  const unsigned n_c = (unsigned)(P * (P - 1) / 2);
+  unsigned n2 = 2u;
+  while (n2 < n_c) n2 <<= 1;
+  if (tid == 0) s_cursor = 0u;
+  for (unsigned i = n_c + tid; i < n2; i += blockDim.x) s_key[i] = ~0ull;
+  __syncthreads();
+  hd_sweep(s_x, P, 0, 1, [&](bool on, double d2) {
+    if (on) s_key[atomicAdd(&s_cursor, 1u)] = (unsigned long long)__double_as_longlong(d2);
+  });
+  __syncthreads();
+  for (unsigned k = 2u; k <= n2; k <<= 1)
+    for (unsigned j = k >> 1; j > 0u; j >>= 1) {
+      for (unsigned i = tid; i < n2; i += blockDim.x) {
+        const unsigned o = i ^ j;
+        if (o > i) {
+          const unsigned long long u = s_key[i], v = s_key[o];
+          if (((i & k) == 0u) ? (u > v) : (u < v)) { s_key[i] = v; s_key[o] = u; }
+        }
+      }
       __syncthreads();
-      double *s_list = reinterpret_cast<double *>(s_hist);
-      hd_fast_gather(s_x, P, w, (unsigned)tbin, s_list, &s_cursor, 0, 1);
-      __syncthreads();
-      const unsigned n_c = s_cursor;
-      if (n_c >= 1u && n_c <= (unsigned)HD_COLLECT_CAP) have = hd_pick(s_list, n_c, (unsigned)(trank >> 1), &s_val, &s_found, &median);
     }
+  if (tid == 0) {
+    const unsigned long long rank0 = ((unsigned long long)P * (unsigned long long)P - 1ull) / 2ull;  // lower median of P^2 entries
+    const unsigned long long key = rank0 < (unsigned long long)P ? 0ull : s_key[(rank0 - (unsigned long long)P) / 2ull];
+    c->bandwidth = __longlong_as_double((long long)key) / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
   }
-  if (!have) {
-    unsigned long long prefix = 0ull, rank = rank0;
-    for (int ps = 0; ps < MED_PASSES; ps++) {
-      const int nb = 1 << hd_pass_bits(ps);
-      __syncthreads();
-      for (int i = tid; i < nb; i += blockDim.x) s_hist[i] = 0u;
-      __syncthreads();
-      hd_radix_hist(s_x, P, ps, prefix, s_hist, 0, 1);
-      __syncthreads();
-      for (int i = tid; i < nb; i += blockDim.x) a.hist[i] = s_hist[i];
-      __syncthreads();
-      hd_select(a.hist, prefix, rank, nb, hd_pass_bits(ps), &prefix, &rank, s_warp, s_res);
-    }
-    median = __longlong_as_double((long long)prefix);
-  }
-  if (tid == 0) c->bandwidth = median / log((double)(P + 1));  // SVNICP.cpp:262 (Q4)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -352,6 +352,39 @@ def test_align_twice_without_add_cloud(oracle, small, cls, es):
         assert np.isfinite(p2).all() and np.abs(p2 - p1).max() > 0
 
 
+@pytest.mark.parametrize("P,full,es,flags", [(30, False, True, sv.FLAG_FORCE_GRAPH), (100, True, False, 0), (65, True, True, sv.FLAG_FORCE_GRAPH),
+                                             (300, True, False, sv.FLAG_FORCE_GRAPH), (40, True, False, sv.FLAG_FILTER_FULL)])
+def test_graph_replay_equals_direct_launches(lidar, P, full, es, flags):
+    """Small problems replay iterations >= 1 as CUDA graphs (capi.cu: align_step).  Same kernels, same arguments: the results
+    must be bit-identical to the direct launches (SVNICP_FLAG_NO_GRAPH), also on the second scan of a handle (the graphs of
+    the first scan are patched in place) and with another initial mean."""
+    rng = np.random.default_rng(P)
+    init = synth.init_particles(P, rng)
+    src = lidar.source[::5]
+    out = {}
+    for name, fl in (("graph", flags), ("direct", flags | sv.FLAG_NO_GRAPH)):
+        prm = sv.SteinICPParam(iterations=18, KNN_count=48, max_dist=3.0, lr=1.0, SVN_full_grad=full, check_early_stop=es,
+                               convergence_threshold=2e-3, flags=fl)
+        icp = sv.SVNICP(prm, init)
+        res = []
+        for k in range(3):
+            icp.add_cloud(src[k::2], lidar.target, init)
+            t0 = lidar.t0 + np.array([0.01 * k, -0.02 * k, 0.0])
+            icp.set_initial_mean(lidar.R0, t0)
+            assert icp.stein_align() == sv.ALIGN_SUCCESS
+            res.append((icp.get_particles().copy(), icp.get_particle_history().copy(), icp.iterations_done(), icp.get_cov_matrix().copy(),
+                        icp.launch_count()))
+        out[name] = res
+        icp.close()
+    for g, d in zip(out["graph"], out["direct"]):
+        assert g[2] == d[2]
+        if not es:  # with early stop the number of no-op iterations enqueued behind the stop may differ by one
+            assert g[4] == d[4]
+        np.testing.assert_array_equal(g[0], d[0])
+        np.testing.assert_array_equal(g[1], d[1])
+        np.testing.assert_array_equal(g[3], d[3])
+
+
 def test_set_k_keeps_the_clouds(oracle, small):
     """set_k (SVGDICP.h:98) only changes K_source_: the next stein_align uses the new K on the stored clouds."""
     icp = make_icp(small, iterations=0, KNN_count=20, max_dist=3.0, debug_corr=True)
