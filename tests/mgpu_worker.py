@@ -30,7 +30,7 @@ def main():
              (256, True, False, "svn", 0, False), (300, False, True, "svn", 0, False), (256, True, False, "svn", sv.FLAG_NO_PARTICLE_SORT, False),
              (200, True, False, "svn", sv.FLAG_NCCL_GATHER, False), (130, True, True, "svn", sv.FLAG_NCCL_GATHER, False),
              (160, True, False, "svn", 0, True),
-             (48, True, False, "svgd", 0, False), (41, True, True, "svgd", 0, False))
+             (48, True, False, "svgd", 0, False), (43, True, True, "svgd", 0, False))
     for P, full, es, cls, flags, twice in cases:
         pb = synth.make_problem(P, sensor="32", scan_index=6, n_map_scans=6, seed=0xC0FFEE)
         if cls == "svn":
