@@ -11,7 +11,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pb = synth.make_problem_saturated(P, sensor="64")
-VARIANTS = (("default", 0), ("nccl_gather", sv.FLAG_NCCL_GATHER), ("no_sort", sv.FLAG_NO_PARTICLE_SORT), ("filter_full", sv.FLAG_FILTER_FULL))
+VARIANTS = (("default", 0), ("peer", sv.FLAG_PEER_EXCHANGE), ("nccl_gather", sv.FLAG_NCCL_GATHER), ("no_sort", sv.FLAG_NO_PARTICLE_SORT), ("filter_full", sv.FLAG_FILTER_FULL))
 if len(sys.argv) > 3:
     VARIANTS = tuple(v for v in VARIANTS if v[0] in sys.argv[3].split(","))
 for name, fl in VARIANTS:
@@ -20,7 +20,7 @@ for name, fl in VARIANTS:
     uid = [sv.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     icp.init_sharding(uid[0], rank, world)
-    for _ in range(2):
+    for _ in range(3):
         icp.add_cloud(pb.source, pb.target, pb.init_pose); icp.set_initial_mean(pb.R0, pb.t0)
         assert icp.stein_align() == sv.ALIGN_SUCCESS
     got, hist, mean = icp.get_particles().reshape(6, -1).copy(), icp.get_particle_history().copy(), icp.get_transformation().copy()

@@ -823,6 +823,7 @@ static int align_begin(svnicp_handle h, AlignState &S) {
   // finalize -> ncclAllGather of the records -> k_head -> k_tail, all on the main stream.
   const bool overlap = S.overlap = !svgd && (h->n_ranks == 1 || h->peer_mode);
   S.pt = h->pt;  // n_ranks == 1 view unless the peer exchange is up
+  S.seq0 = h->seq;  // sequence numbers of the peer exchange run on across scans (stale flags of the last scan must never satisfy a wait)
   // Small problems without early stop are bound by the host's enqueue rate (~13 API calls per iteration against ~50 us of
   // kernels), so iterations >= 1 are captured once per scan into one CUDA graph per list-buffer parity and replayed with one
   // launch each.  Same kernels, same arguments, same order.  Measured on 868-point scans: 100 particles x 30 iterations 3.49 ->

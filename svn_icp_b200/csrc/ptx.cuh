@@ -74,10 +74,14 @@ __device__ __forceinline__ void peer_wait(const PeerTable &pt, int kind, unsigne
   if (pt.n_ranks > 1 && (int)threadIdx.x < pt.n_ranks && (int)threadIdx.x != pt.rank) {
     const unsigned *f = pt.flag[pt.rank] + kind * MAX_RANKS + threadIdx.x;
     const unsigned long long t0 = global_timer_ns();
-    while ((int)(ld_acquire_sys(f) - seq) < 0) {
+    unsigned v;
+    while ((int)((v = ld_acquire_sys(f)) - seq) < 0) {
       if (global_timer_ns() - t0 > pt.timeout_ns) { atomicExch(&c->error, 1); break; }
       __nanosleep(64);
     }
+    // a peer is never more than one iteration ahead: a flag beyond seq + 1 means the ranks disagree on the sequence numbers
+    // (e.g. they restarted with a scan) and the waits protect nothing -- caught by the debug build
+    SVN_CHECK(c, (int)(v - seq) <= 1 || (int)(v - seq) < 0, 40);
   }
   __syncthreads();
 }
