@@ -87,8 +87,6 @@ typedef struct {
 #define SVNICP_FLAG_NO_GRAPH 128        /* never replay iterations as CUDA graphs (A/B measurements)                      */
 #define SVNICP_FLAG_FORCE_GRAPH 256     /* replay iterations >= 1 as CUDA graphs whatever the problem size (default: only
                                            unsharded SVN-ICP handles without early stop and N_s * P <= 1e7: host-enqueue bound) */
-#define SVNICP_FLAG_PEER_EXCHANGE 512    /* sharded over MORE than two ranks: use the peer-memory record exchange (default there:
-                                           one ncclAllGather per iteration; see svnicp_init_sharding)                      */
 #define SVNICP_FLAG_REUSE_STATS 16      /* svnicp_get_prune_stats reports the fraction of rows served by list reuse    */
 
 /* Fill with the defaults of SteinICPParam (SVGDICP.h:41-57). */
@@ -114,10 +112,10 @@ const char *svnicp_last_error(svnicp_handle h); /* h may be NULL: last creation 
 int svnicp_set_stream(svnicp_handle h, void *cuda_stream);
 
 /* Particle sharding across the GPUs of one box (no reference counterpart):
- * every rank owns particles [rank*P/n, (rank+1)*P/n).  SVN-ICP class on TWO ranks (or with SVNICP_FLAG_PEER_EXCHANGE): the
- * ranks map each other's record buffers through CUDA IPC and the owner of a particle stores its record straight into every
- * peer over NVLink (no collective call per iteration; needs one process per GPU); more than two ranks, a failed IPC set-up,
- * SVNICP_FLAG_NCCL_GATHER and the SVGD-ICP class: one ncclAllGather per iteration carries the packed per-particle records.  unique_id: 128 bytes from svnicp_nccl_unique_id on rank 0,
+ * every rank owns particles [rank*P/n, (rank+1)*P/n).  SVN-ICP class: the ranks map each other's record buffers through
+ * CUDA IPC and the owner of a particle stores its record straight into every peer over NVLink (no collective call per
+ * iteration; needs one process per GPU); if that cannot be set up, or with SVNICP_FLAG_NCCL_GATHER, and for the SVGD-ICP
+ * class, one ncclAllGather per iteration carries the packed per-particle records instead.  unique_id: 128 bytes from svnicp_nccl_unique_id on rank 0,
  * distributed by the caller (MPI / torch.distributed / files).  libnccl.so.2 is dlopen'ed. */
 int svnicp_nccl_unique_id(void *id128);
 int svnicp_init_sharding(svnicp_handle h, const void *unique_id128, int rank, int n_ranks);

@@ -11,7 +11,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pb = synth.make_problem_saturated(P, sensor="64")
-VARIANTS = (("default", 0), ("peer", sv.FLAG_PEER_EXCHANGE), ("nccl_gather", sv.FLAG_NCCL_GATHER), ("no_sort", sv.FLAG_NO_PARTICLE_SORT), ("filter_full", sv.FLAG_FILTER_FULL))
+VARIANTS = (("default", 0), ("nccl_gather", sv.FLAG_NCCL_GATHER), ("no_sort", sv.FLAG_NO_PARTICLE_SORT), ("filter_full", sv.FLAG_FILTER_FULL))
 if len(sys.argv) > 3:
     VARIANTS = tuple(v for v in VARIANTS if v[0] in sys.argv[3].split(","))
 for name, fl in VARIANTS:

@@ -48,7 +48,6 @@ FLAG_DEBUG_SYNC = 32
 FLAG_WATCHDOG = 64
 FLAG_NO_GRAPH = 128
 FLAG_FORCE_GRAPH = 256
-FLAG_PEER_EXCHANGE = 512
 
 
 @dataclasses.dataclass

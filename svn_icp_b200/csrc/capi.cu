@@ -498,12 +498,7 @@ int svnicp_init_sharding(svnicp_handle h, const void *unique_id128, int rank, in
   if (r) return r;
   h->have_cloud = false;
   h->peer_mode = false;
-  // The peer-memory exchange is the default for TWO ranks only.  With the final kernels of round 2 it reproduced the single-GPU
-  // scan on 2 GPUs in every run (<= 8e-6 at configs[1], the level of the summation-order effects), but on 8 GPUs repeated scans
-  // on one handle came out 4e-4 .. 9e-3 off from iteration 1 on (scripts/mgpu_probe.py; the ncclAllGather path was exact in the
-  // same run).  Until that is understood, more than two ranks exchange through NCCL unless SVNICP_FLAG_PEER_EXCHANGE asks otherwise.
-  const bool want_peer = !(h->prm.flags & SVNICP_FLAG_NCCL_GATHER) && (n_ranks == 2 || (h->prm.flags & SVNICP_FLAG_PEER_EXCHANGE));
-  if (n_ranks > 1 && n_ranks <= MAX_RANKS && h->class_type == SVNICP_CLASS_SVNICP && want_peer) {
+  if (n_ranks > 1 && n_ranks <= MAX_RANKS && h->class_type == SVNICP_CLASS_SVNICP && !(h->prm.flags & SVNICP_FLAG_NCCL_GATHER)) {
     // Peer-memory exchange: map every rank's record block here through CUDA IPC (handles travel over the NCCL communicator
     // that exists anyway).  Any failure on any rank -> all ranks fall back to one ncclAllGather per iteration.
     struct Slot { cudaIpcMemHandle_t hdl; int ok; int pad[15]; };
