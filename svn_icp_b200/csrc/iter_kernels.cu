@@ -13,9 +13,10 @@
 //              the centre query), in slot order.  Reads 16*N_s*(K+1) bytes: the HBM-roofline kernel.
 //   k_gn       fused transform + 1-NN over the pruned lists + robust weight + Gauss-Newton reduction.
 //              Lists are staged through shared memory with 1-D TMA bulk copies (cp.async.bulk +
-//              mbarrier, a dedicated producer warp, S stages); one thread owns one particle and keeps
-//              its 16 sums in registers (fp32 per tile, folded into fp64), so no cross-thread reduction
-//              is needed until the per-CTA partials are summed by k_finalize.
+//              mbarrier, S stages, the 16 warps of the CTA take turns as producer); one thread owns TWO
+//              particles in packed fp32 pairs (FFMA2 / FADD2 / FMUL2) and keeps their 16 sums in registers
+//              (fp32 per 32 rows, folded into fp32 shared-memory slots, then fp64), so no cross-thread
+//              reduction is needed until the per-CTA partials are summed by k_finalize.
 //   k_finalize fixed-order fp64 sum of the partials -> H (21), b (6) of the reference's system.
 //
 // Arithmetic that decides a correspondence index is written with explicit _rn intrinsics and is restated
@@ -477,7 +478,7 @@ __device__ __forceinline__ void gn_recover(const float4 *e, int bk, float qx, fl
 // pairs (nonzero_count, :404) and the second-moment sums 1..9 are not needed -- the gradient is E and C alone because
 // every Euler partial is [omega_k]x R (see svgd_class.cu).
 // Stage layout: [TB][Kp] float4 pruned lists, then [TB] float4 row headers (source point R0 s, w = list length bits: padded
-// length << 16 | true length; 0 = padding row), then three 32-bit row masks written by the producer warp: rows whose padded list
+// length << 16 | true length; 0 = padding row), then three 32-bit row masks written by the warp that loads the tile: rows whose padded list
 // length is 2, 4, and more.  The consumers walk the three classes one after the other with a loop body specialised for the
 // class (no data-dependent branch inside the two short-list bodies: control flow was 18 of 122 instructions per row).
 // Thread -> particles: consumer thread pl of particle group y carries particles 2*(y*PG + pl) and the next one (neighbours in
