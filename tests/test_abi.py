@@ -77,3 +77,17 @@ def test_particle_initialisers(lib):
     assert np.all(np.abs(g) <= 3 * sd[:, None] + 1e-15)
     np.testing.assert_allclose(g.std(axis=1), sd, rtol=0.08)
     np.testing.assert_array_equal(sv.initialize_particles_gaussian(1, cov), np.zeros((6, 1)))
+
+
+def test_flag_constants_mirror_the_header():
+    """Every SVNICP_FLAG_* of include/svnicp_b200.h has a Python twin FLAG_* with the same value, the values are distinct bits,
+    and the debug-build switch of the loader is an explicit path (never a silent fallback)."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "svnicp_b200.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SVNICP_FLAG_(\w+)\s+(\d+)", hdr)}
+    assert len(flags) >= 8
+    for name, value in flags.items():
+        assert getattr(sv, "FLAG_" + name) == value, name
+        assert value & (value - 1) == 0, f"{name} is not a single bit"
+    assert len(set(flags.values())) == len(flags)
+    assert sv.LIB_PATH.endswith(".so")
