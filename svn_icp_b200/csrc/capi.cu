@@ -88,6 +88,7 @@ struct svnicp_handle_t {
   // small problems: iterations >= 1 run as two CUDA graphs (one per list-buffer parity), see align_step
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   int glaunches[2] = {0, 0};
+  bool graph_off = false;  // a capture failed once: direct launches for the rest of the handle's life
   cudaEvent_t ev_cfork = nullptr, ev_chead = nullptr;
   // record block: [2][rec_stride] doubles (double buffered by iteration parity) + the peer-exchange flag block; one cudaMalloc,
   // exported to the other ranks through CUDA IPC when sharded
@@ -825,7 +826,7 @@ static int align_begin(svnicp_handle h, AlignState &S) {
   // 3.00 ms; with early stop (the host follows the stop flag three iterations behind, so it is never the bottleneck) the two
   // captures per scan cost more than they save (4.15 -> 4.49 ms), and big problems have nothing to gain: both keep the direct
   // launches, and the per-phase events stay usable.
-  S.use_graph = overlap && h->n_ranks == 1 && !h->profile && !h->prm.debug_corr &&
+  S.use_graph = overlap && h->n_ranks == 1 && !h->profile && !h->prm.debug_corr && !h->graph_off &&
                 !(h->prm.flags & (SVNICP_FLAG_DEBUG_SYNC | SVNICP_FLAG_NO_GRAPH)) &&
                 ((h->prm.flags & SVNICP_FLAG_FORCE_GRAPH) || (!h->prm.check_early_stop && I >= 16 && (double)h->n_s * (double)h->P_l <= 1.0e7));
 
@@ -884,46 +885,49 @@ static int align_step(svnicp_handle h, AlignState &S) {
         }
         cudaGraph_t g = nullptr;
         int n = 0;
-        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-        bool ok = cudaEventRecord(h->ev_cfork, st) == cudaSuccess && cudaStreamWaitEvent(hs, h->ev_cfork, 0) == cudaSuccess;
-        const int nh = ok ? launch_head(sa, pt, 0u, 0, hs) : -1;
-        ok = ok && nh >= 0 && cudaEventRecord(h->ev_chead, hs) == cudaSuccess;
+        bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
         if (ok) {
-          n = nh + launch_filter(ia, st) + launch_gn(ia, st) + launch_finalize(ia, pt, 0u, st);
-          ok = cudaStreamWaitEvent(st, h->ev_chead, 0) == cudaSuccess;
-          n += launch_tail(sa, ia, pt, 0u, 0u, st);
+          ok = cudaEventRecord(h->ev_cfork, st) == cudaSuccess && cudaStreamWaitEvent(hs, h->ev_cfork, 0) == cudaSuccess;
+          const int nh = ok ? launch_head(sa, pt, 0u, 0, hs) : -1;
+          ok = ok && nh >= 0 && cudaEventRecord(h->ev_chead, hs) == cudaSuccess;
+          if (ok) {
+            n = nh + launch_filter(ia, st) + launch_gn(ia, st) + launch_finalize(ia, pt, 0u, st);
+            ok = cudaStreamWaitEvent(st, h->ev_chead, 0) == cudaSuccess;
+            n += launch_tail(sa, ia, pt, 0u, 0u, st);
+          }
+          ok = (cudaStreamEndCapture(st, &g) == cudaSuccess) && ok && g;  // always end the capture, also after a failure inside it
         }
-        const cudaError_t ce = cudaStreamEndCapture(st, &g);  // always end the capture, also after a failure inside it
-        if (!ok || ce != cudaSuccess || !g) {
-          if (g) cudaGraphDestroy(g);
-          cudaGetLastError();
-          return fail(h, SVNICP_ERR_CUDA, "capture of the iteration graph failed: %s", cudaGetErrorString(ce));
-        }
-        if (h->gexec[par]) {  // same topology as the last scan's: patch the arguments in place
+        if (ok && h->gexec[par]) {  // same topology as the last scan's: patch the arguments in place
           cudaGraphExecUpdateResultInfo info;
           if (cudaGraphExecUpdate(h->gexec[par], g, &info) != cudaSuccess) {
-            cudaGetLastError();
             cudaGraphExecDestroy(h->gexec[par]);
             h->gexec[par] = nullptr;
           }
         }
-        if (!h->gexec[par]) {
-          const cudaError_t ie = cudaGraphInstantiate(&h->gexec[par], g, 0);
-          if (ie != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SVNICP_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
-        }
-        cudaGraphDestroy(g);
+        if (ok && !h->gexec[par]) ok = cudaGraphInstantiate(&h->gexec[par], g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();  // a failed capture / update / instantiation is not an error of the scan (see below)
         h->glaunches[par] = n;
-        S.graph_ready[par] = true;
+        S.graph_ready[par] = ok;
       }
-      CU(cudaGraphLaunch(h->gexec[par], st));
-      h->launches += h->glaunches[par];
-      if (h->prm.check_early_stop) {
-        CU(cudaMemcpyAsync(&h->h_stop[e], &h->ctrl.p->stop, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaEventRecord(h->iter_events[e], st));
+      if (S.graph_ready[par]) {
+        CU(cudaGraphLaunch(h->gexec[par], st));
+        h->launches += h->glaunches[par];
+        if (h->prm.check_early_stop) {
+          CU(cudaMemcpyAsync(&h->h_stop[e], &h->ctrl.p->stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+          CU(cudaEventRecord(h->iter_events[e], st));
+        }
+        S.e = e + 1;
+        if (S.e >= I) S.enqueue_done = true;
+        return SVNICP_OK;
       }
-      S.e = e + 1;
-      if (S.e >= I) S.enqueue_done = true;
-      return SVNICP_OK;
+      // The graph could not be built (e.g. a caller's stream that cannot be captured): this handle keeps the direct launches
+      // of the same kernels from here on.  Nothing captured was executed; the head chain below must wait for everything
+      // enqueued so far, hence a fresh ev_x.
+      S.use_graph = false;
+      h->graph_off = true;
+      if (h->gexec[par]) { cudaGraphExecDestroy(h->gexec[par]); h->gexec[par] = nullptr; }
+      CU(cudaEventRecord(h->ev_x, st));
     }
     PROF(0);
     if (svgd) h->launches += launch_prep(ia, st, 0, nullptr);
